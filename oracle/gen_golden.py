@@ -1,0 +1,344 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_harness.py) on fixed seeds with its RNG sources redirected to
+the Philox lane streams.  Run in the build container (the reference cannot travel to the GPU box):
+
+    python -m oracle.gen_golden            # rewrites tests/golden/
+
+The fixtures pin (a) the C restatement oracle/le_oracle.c (tests/test_oracle_vs_golden.py, CPU) and
+(b) the CUDA path (tests/test_gpu_*.py, GPU) to the reference's own outputs.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from learning_environments_b200 import config as le_config  # noqa: E402
+from learning_environments_b200._abi import ENV_SE, ENV_RN, ENV_REAL  # noqa: E402
+
+
+def cfg_bytes(cfg, agent_name, env_kind, **kw):
+    """le_lane_cfg bytes: the fixtures must be self-contained (the YAML files do not exist on the GPU box)."""
+    c = le_config.lane_cfg(cfg, agent_name=agent_name, env_kind=env_kind, **kw)
+    return np.frombuffer(bytes(c), dtype=np.uint8).copy()
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def linear_params(module):
+    """Concatenate nn.Linear weights/biases in module order (the parameter vector 'theta' of le_b200.h)."""
+    import torch.nn as nn
+    out = []
+    for l in module.modules():
+        if isinstance(l, nn.Linear):
+            out.append(l.weight.detach().numpy().reshape(-1))
+            if l.bias is not None:
+                out.append(l.bias.detach().numpy().reshape(-1))
+    return np.concatenate(out).astype(np.float32)
+
+
+def small_config(name, **agent_overrides):
+    cfg = rh.load_reference_yaml(name)
+    agent = cfg["agents"]["gtn"]["agent_name"].lower()
+    cfg["agents"][agent].update(agent_overrides)
+    cfg["agents"][agent]["print_rate"] = 10 ** 9
+    return cfg, agent
+
+
+# ------------------------------------------------------------------------------------------------------
+def gen_se_step(yaml_name, tag, seed):
+    import torch
+    mods = rh.import_reference()
+    cfg = rh.load_reference_yaml(yaml_name)
+    torch.manual_seed(seed)
+    fac = mods["envs.env_factory"].EnvFactory(cfg)
+    venv = fac.generate_virtual_env()
+    sd, ad = venv.get_state_dim(), venv.get_action_dim()
+    rng = np.random.RandomState(seed)
+    n = 64
+    states = rng.uniform(-1.0, 1.0, size=(n, sd)).astype(np.float32)
+    actions = rng.randint(0, ad, size=n).astype(np.int32)
+    ns = np.zeros((n, sd), np.float32)
+    rew = np.zeros(n, np.float32)
+    done = np.zeros(n, np.float32)
+    with torch.no_grad():
+        for i in range(n):
+            # the single-agent call of agents/base_agent.py:117: EnvWrapper.step(action) on env.state
+            venv.env.state = torch.from_numpy(states[i])
+            a = torch.tensor([actions[i]], dtype=torch.float32)
+            s2, r, d = venv.step(action=a)
+            ns[i], rew[i], done[i] = s2.numpy(), r.item(), d.item()
+        # the batched entry (envs/virtual_env.py:45-47, histogram experiment): state passed explicitly
+        s2b, rb, db = venv.step(action=torch.from_numpy(actions.astype(np.float32)), state=torch.from_numpy(states))
+    assert np.allclose(s2b.numpy(), ns, atol=1e-6)
+    np.savez(os.path.join(GOLDEN, "se_step_%s.npz" % tag), theta=linear_params(venv), states=states, actions=actions,
+             next_states=ns, rewards=rew, dones=done, yaml=yaml_name,
+             cfg=cfg_bytes(cfg, cfg["agents"]["gtn"]["agent_name"].lower(), ENV_SE))
+
+
+def gen_rn_reward(seed):
+    import torch
+    mods = rh.import_reference()
+    yaml_name = "default_config_cartpole_reward_env.yaml"
+    rng = np.random.RandomState(seed)
+    n = 32
+    s = rng.uniform(-1, 1, size=(n, 4))
+    s2 = rng.uniform(-1, 1, size=(n, 4))
+    rr = rng.uniform(-1, 2, size=n)
+    out = {}
+    theta = None
+    for t in (0, 1, 2, 5, 6):
+        cfg = rh.load_reference_yaml(yaml_name)
+        cfg["envs"]["CartPole-v0"]["reward_env_type"] = t
+        torch.manual_seed(seed)
+        fac = mods["envs.env_factory"].EnvFactory(cfg)
+        renv = fac.generate_reward_env()
+        renv.set_agent_params(same_action_num=1, gamma=0.99)
+        if t != 0:
+            th = linear_params(renv)
+            if theta is None:
+                theta = th
+            assert np.array_equal(theta, th)
+        res = np.zeros(n, np.float32)
+        with torch.no_grad():
+            for i in range(n):
+                res[i] = np.float32(renv.env._calc_reward(state=s[i], next_state=s2[i], reward=rr[i], info={}))
+        out["type%d" % t] = res
+    np.savez(os.path.join(GOLDEN, "rn_reward_cartpole.npz"), theta=theta, s=s, s2=s2, real_reward=rr, gamma=0.99,
+             yaml=yaml_name, cfg=cfg_bytes(cfg, "ddqn", ENV_RN, gamma=0.99), **out)
+
+
+def gen_td_update(yaml_name, tag, seed, steps=5):
+    """DDQN.learn (agents/DDQN.py:60-95) `steps` times on explicit minibatches."""
+    import torch
+    mods = rh.import_reference()
+    cfg, agent_name = small_config(yaml_name)
+    torch.manual_seed(seed)
+    fac = mods["envs.env_factory"].EnvFactory(cfg)
+    real_env = fac.generate_real_env()
+    agent = mods["agents.agent_utils"].select_agent(cfg, cfg["agents"]["gtn"]["agent_name"])
+    sd, ad, B = agent.state_dim, agent.action_dim, agent.batch_size
+    rng = np.random.RandomState(seed)
+    rows = np.zeros((steps, B, 2 * sd + 3), np.float32)
+    rows[:, :, :sd] = rng.uniform(-1, 1, size=(steps, B, sd))
+    rows[:, :, sd] = rng.randint(0, ad, size=(steps, B))
+    rows[:, :, sd + 1:2 * sd + 1] = rng.uniform(-1, 1, size=(steps, B, sd))
+    rows[:, :, 2 * sd + 1] = rng.uniform(-1, 1, size=(steps, B))
+    rows[:, :, 2 * sd + 2] = (rng.uniform(size=(steps, B)) < 0.1) * 1.0 + rng.uniform(-0.05, 0.05, size=(steps, B))
+
+    class FakeRB(object):
+        def __init__(self):
+            self.k = 0
+
+        def sample(self, batch_size):
+            r = torch.from_numpy(rows[self.k])
+            self.k += 1
+            return (r[:, :sd], r[:, sd:sd + 1], r[:, sd + 1:2 * sd + 1], r[:, 2 * sd + 1:2 * sd + 2], r[:, 2 * sd + 2:])
+
+    q0 = linear_params(agent.model)
+    rb = FakeRB()
+    thetas, targets, losses = [], [], []
+    for k in range(steps):
+        loss = agent.learn(replay_buffer=rb, env=real_env, episode=10)
+        losses.append(loss.item())
+        thetas.append(linear_params(agent.model))
+        targets.append(linear_params(agent.model_target))
+    st = agent.optimizer.state_dict()["state"]
+    m = np.concatenate([st[i]["exp_avg"].numpy().reshape(-1) for i in range(4)])
+    v = np.concatenate([st[i]["exp_avg_sq"].numpy().reshape(-1) for i in range(4)])
+    np.savez(os.path.join(GOLDEN, "td_update_%s.npz" % tag), q_init=q0, rows=rows, thetas=np.stack(thetas),
+             targets=np.stack(targets), losses=np.array(losses, np.float32), adam_m=m, adam_v=v, yaml=yaml_name,
+             cfg=cfg_bytes(cfg, agent_name, ENV_RN if "reward_env" in yaml_name else ENV_SE))
+
+
+def gen_real_env(seed):
+    """Trajectories of the gym stand-in (oracle/stubs/gym) — pins the C/CUDA dynamics to the restated equations."""
+    import gym
+    rng = np.random.RandomState(seed)
+    for name, tag, nact in (("CartPole-v0", "cartpole", 2), ("Acrobot-v1", "acrobot", 3)):
+        env = gym.make(name)
+        eps = []
+        for ep in range(4):
+            st0 = rng.uniform(-0.05, 0.05, size=4) if tag == "cartpole" else rng.uniform(-0.1, 0.1, size=4)
+            env.unwrapped.reset_hook = lambda e, s=st0: s
+            obs0 = env.reset()
+            T = 60 if tag == "cartpole" else 120
+            acts = rng.randint(0, nact, size=T)
+            states, obs, rew, done = [np.array(env.unwrapped.state, np.float64)], [obs0], [], []
+            for a in acts:
+                o, r, d, _ = env.step(int(a))
+                states.append(np.array(env.unwrapped.state, np.float64))
+                obs.append(o)
+                rew.append(r)
+                done.append(d)
+                if d:
+                    break
+            eps.append(dict(actions=acts[:len(rew)], states=np.stack(states), obs=np.stack(obs), rewards=np.array(rew),
+                            dones=np.array(done)))
+        flat = {}
+        for i, e in enumerate(eps):
+            for k, v in e.items():
+                flat["ep%d_%s" % (i, k)] = v
+        np.savez(os.path.join(GOLDEN, "real_env_%s.npz" % tag), n_episodes=len(eps), **flat)
+
+
+def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, use_test_env=True):
+    """Full BaseAgent.train(+test) of the reference under RNG injection; per-step trace of the first steps."""
+    import torch
+    mods = rh.import_reference()
+    cfg, agent_name = small_config(yaml_name, **overrides)
+    torch.manual_seed(seed)
+    fac = mods["envs.env_factory"].EnvFactory(cfg)
+    real_env = fac.generate_real_env()
+    if env_kind == "se":
+        train_env = fac.generate_virtual_env()
+        env_theta = linear_params(train_env)
+        reset_envs = [train_env.env.reset_env.env.unwrapped, real_env.env.unwrapped]
+        spaces = [train_env.env.action_space]
+    elif env_kind == "rn":
+        train_env = fac.generate_reward_env()
+        env_theta = linear_params(train_env)
+        reset_envs = [train_env.env.real_env.unwrapped, real_env.env.unwrapped]
+        spaces = [train_env.env.action_space]
+    else:
+        train_env = fac.generate_real_env()
+        env_theta = np.zeros(1, np.float32)
+        reset_envs = [train_env.env.unwrapped, real_env.env.unwrapped]
+        spaces = [train_env.env.action_space]
+    agent = mods["agents.agent_utils"].select_agent(cfg, cfg["agents"]["gtn"]["agent_name"])
+    q_init = linear_params(agent.model)
+    sd, ad = agent.state_dim, agent.action_dim
+    inj = rh.LaneRngInjector(key, ad, "cartpole" if "CartPole" in cfg["env_name"] else "acrobot")
+
+    tr = dict(action=[], explore=[], next_state=[], reward=[], done=[], loss=[])
+    orig_learn, orig_select, orig_step = agent.learn, agent.select_train_action, train_env.step
+    state_now = {"explore": 0}
+
+    def learn(replay_buffer, env, episode):
+        loss = orig_learn(replay_buffer=replay_buffer, env=env, episode=episode)
+        tr["loss"][-1] = float(loss.item())
+        return loss
+
+    def select(state, env, episode):
+        before = inj.train_steps
+        a = orig_select(state=state, env=env, episode=episode)
+        assert inj.train_steps == before + 1
+        u = float(inj._act_words[0] >> 8) / 16777216.0
+        tr["explore"].append(1 if u < agent.eps else 0)
+        return a
+
+    def step(action, state=None):
+        s2, r, d = orig_step(action=action) if state is None else orig_step(action=action, state=state)
+        tr["action"].append(int(action.reshape(-1)[0].item()))
+        tr["next_state"].append(s2.detach().numpy().astype(np.float32).copy())
+        tr["reward"].append(float(r))
+        tr["done"].append(float(d))
+        tr["loss"].append(float("nan"))
+        return s2, r, d
+
+    agent.learn, agent.select_train_action, train_env.step = learn, select, step
+    with rh.injected_rng(inj, reset_envs=reset_envs, action_spaces=spaces):
+        rewards, lengths, _ = agent.train(env=train_env, test_env=real_env if use_test_env else None)
+        test_rewards, _, _ = agent.test(env=real_env)
+    n = min(trace_cap, len(tr["action"]))
+    kind_id = {"se": ENV_SE, "rn": ENV_RN, "real": ENV_REAL}[env_kind]
+    np.savez(os.path.join(GOLDEN, "trajectory_%s.npz" % tag), yaml=yaml_name, env_kind=env_kind, key=np.array(key, np.uint32),
+             cfg=cfg_bytes(cfg, agent_name, kind_id, use_test_env=use_test_env, final_test=True),
+             overrides_keys=np.array(list(overrides.keys())), overrides_vals=np.array([float(v) for v in overrides.values()]),
+             use_test_env=int(use_test_env), env_theta=env_theta, q_init=q_init, q_final=linear_params(agent.model),
+             rewards=np.array(rewards, np.float64), lengths=np.array(lengths, np.int32),
+             test_rewards=np.array(test_rewards, np.float64), train_steps=len(tr["action"]), learn_iters=inj.learn_iters,
+             action=np.array(tr["action"][:n], np.int32), explore=np.array(tr["explore"][:n], np.int32),
+             next_state=np.stack(tr["next_state"][:n]), reward=np.array(tr["reward"][:n], np.float32),
+             done=np.array(tr["done"][:n], np.float32), loss=np.array(tr["loss"][:n], np.float32),
+             sample0=inj.sample_log[0] if inj.sample_log else np.zeros(0, np.int32))
+    print("trajectory", tag, "episodes", len(rewards), "steps", len(tr["action"]), "learn", inj.learn_iters, "rewards",
+          rewards[:4], "test", test_rewards[:3])
+
+
+def gen_nes(seed):
+    """GTN_Master.score_transform (agents/GTN_master.py:197-265) for all 8 types, and update_env (:267-298)."""
+    import torch
+    mods = rh.import_reference()
+    cfg = rh.load_reference_yaml("default_config_cartpole_syn_env.yaml")
+    cfg["agents"]["gtn"]["num_workers"] = 8
+    rng = np.random.RandomState(seed)
+    score_lists = [
+        [10, 200, 35.5, 9.4, 150, 200, 60, 12],                 # SURVEY Appendix C (tie between members 1 and 5)
+        list(rng.uniform(0, 200, size=8)),
+        [50.0] * 8,                                             # all equal
+        [-500, -100, -480, -90, -500, -250, -100, -499],        # Acrobot-like negative scores with ties
+    ]
+    orig_lists = [[50] * 8, list(rng.uniform(0, 200, size=8)), [50.0] * 8, [-300.0] * 8]
+    out = {}
+    with rh.in_tmp_cwd():
+        torch.manual_seed(seed)
+        master = mods["agents.GTN_master"].GTN_Master(cfg, bohb_id=-1)
+        for li, (sl, ol) in enumerate(zip(score_lists, orig_lists)):
+            out["scores%d" % li] = np.array(sl, np.float64)
+            out["scores_orig%d" % li] = np.array(ol, np.float64)
+            for t in range(8):
+                master.score_transform_type = t
+                master.score_list = list(sl)
+                master.score_orig_list = list(ol)
+                with np.errstate(all="ignore"):
+                    master.score_transform()
+                out["transform%d_type%d" % (li, t)] = np.array(master.score_transform_list, np.float64)
+        # update_env with explicit eps: theta, eps_i, weights -> theta'
+        theta0 = linear_params(master.synthetic_env_orig)
+        P = theta0.size
+        eps = (rng.standard_normal(size=(8, P)) * 0.0124).astype(np.float32)
+        import torch.nn as nn
+        for i in range(8):
+            off = 0
+            for l in master.eps_list[i].modules():
+                if isinstance(l, nn.Linear):
+                    nw = l.weight.numel()
+                    l.weight = nn.Parameter(torch.from_numpy(eps[i, off:off + nw].reshape(l.weight.shape).copy()))
+                    off += nw
+                    nb = l.bias.numel()
+                    l.bias = nn.Parameter(torch.from_numpy(eps[i, off:off + nb].copy()))
+                    off += nb
+            assert off == P
+        for wd, tag in ((0.0, "nowd"), (0.01, "wd")):
+            fresh = mods["agents.GTN_master"].GTN_Master(cfg, bohb_id=-1)
+            fresh.synthetic_env_orig.load_state_dict(master.synthetic_env_orig.state_dict())
+            fresh.eps_list = master.eps_list
+            fresh.weight_decay = wd
+            fresh.score_transform_list = list(out["transform0_type3"])
+            fresh.update_env()
+            out["theta_after_%s" % tag] = linear_params(fresh.synthetic_env_orig)
+    np.savez(os.path.join(GOLDEN, "nes_cartpole.npz"), theta0=theta0, eps=eps, step_size=float(cfg["agents"]["gtn"]["step_size"]),
+             n_lists=len(score_lists), **out)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    import torch
+    torch.set_num_threads(1)
+    gen_se_step("default_config_cartpole_syn_env.yaml", "cartpole", 1)
+    gen_se_step("default_config_acrobot_syn_env.yaml", "acrobot", 2)
+    gen_rn_reward(3)
+    gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole", 4)
+    gen_td_update("default_config_acrobot_syn_env.yaml", "acrobot", 5)
+    gen_td_update("default_config_cartpole_reward_env.yaml", "cartpole_rn", 6)
+    gen_real_env(7)
+    gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se", 11, (0x1234, 0xABCD), "se",
+                   dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)
+    gen_trajectory("default_config_acrobot_syn_env.yaml", "acrobot_se", 12, (0x77, 0x99), "se",
+                   dict(train_episodes=4, test_episodes=2, init_episodes=1), trace_cap=800)
+    gen_trajectory("default_config_cartpole_reward_env.yaml", "cartpole_rn", 13, (0x5, 0x6), "rn",
+                   dict(train_episodes=12, test_episodes=1, init_episodes=2), trace_cap=300)
+    gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se_notest", 14, (0x42, 0x43), "se",
+                   dict(train_episodes=8, test_episodes=3, init_episodes=2, early_out_num=2), trace_cap=200, use_test_env=False)
+    gen_nes(21)
+    print("golden fixtures written to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,518 @@
+/*
+ * le_oracle.c — TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, single-threaded-per-lane CPU restatement of the reference's NES inner loop.  It is the checker
+ * for the CUDA path (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs) and
+ * is never imported, linked or executed by the product package.
+ *
+ * Each function cites the reference file:line (under /root/reference) it follows.  The restatement is pinned
+ * against golden vectors produced by the UNMODIFIED reference under RNG injection (oracle/gen_golden.py ->
+ * tests/golden/, checked in tests/test_oracle_vs_golden.py).  The gym 0.17.3 dynamics are a third-party
+ * dependency absent from /root/reference: restated from the published sources,
+ * "parity unpinned" against upstream gym itself.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction, so fp32/fp64 results follow
+ * torch-eager / CPython operation-by-operation rounding).
+ */
+#include "le_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al. 2011; Random123 constants) — same streams as oracle/philox.py           */
+
+void le_oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static inline uint32_t mulhi32(uint32_t w, uint32_t n) { return (uint32_t)(((uint64_t)w * n) >> 32); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* activations (models/model_utils.py:9-20)                                                            */
+
+static inline float act_f(int act, float slope, float z) {
+    switch (act) {
+        case LE_ACT_TANH: return tanhf(z);
+        case LE_ACT_RELU: return z > 0.f ? z : 0.f;
+        case LE_ACT_LEAKYRELU: return z > 0.f ? z : 0.01f * z;
+        case LE_ACT_PRELU: return z > 0.f ? z : slope * z;
+        default: return z;
+    }
+}
+/* derivative w.r.t. z given z and h = act(z) (autograd of the above) */
+static inline float act_grad(int act, float slope, float z, float h) {
+    switch (act) {
+        case LE_ACT_TANH: return 1.f - h * h;
+        case LE_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case LE_ACT_LEAKYRELU: return z > 0.f ? 1.f : 0.01f;
+        case LE_ACT_PRELU: return z > 0.f ? 1.f : slope;
+        default: return 1.f;
+    }
+}
+
+/* One-hidden-layer MLP, torch layout: W1[H][in], b1[H], W2[out][H], b2[out]
+ * (models/model_utils.py:31-38 with hidden_layer <= 1: Linear, act, Linear). */
+static void mlp_forward(const float* th, int in, int H, int out, int act, float slope, const float* x, float* y,
+                        float* hbuf /* optional [H] */, float* zbuf /* optional [H] */) {
+    const float* W1 = th;
+    const float* b1 = W1 + (size_t)H * in;
+    const float* W2 = b1 + H;
+    const float* b2 = W2 + (size_t)out * H;
+    for (int o = 0; o < out; ++o) y[o] = b2[o];
+    for (int j = 0; j < H; ++j) {
+        float z = b1[j];
+        for (int i = 0; i < in; ++i) z += W1[(size_t)j * in + i] * x[i];
+        float h = act_f(act, slope, z);
+        if (hbuf) hbuf[j] = h;
+        if (zbuf) zbuf[j] = z;
+        for (int o = 0; o < out; ++o) y[o] += W2[(size_t)o * H + j] * h;
+    }
+}
+
+int le_oracle_mlp_params(int in, int H, int out) { return H * in + H + out * H + out; }
+int le_oracle_se_params(const le_lane_cfg* c) {
+    int in = c->sd + c->ad, H = c->env_hidden;
+    return le_oracle_mlp_params(in, H, c->sd) + 2 * le_oracle_mlp_params(in, H, 1);
+}
+int le_oracle_rn_params(const le_lane_cfg* c) { return le_oracle_mlp_params(c->sd, c->env_hidden, 1); }
+int le_oracle_q_params(const le_lane_cfg* c) { return le_oracle_mlp_params(c->sd, c->q_hidden, c->ad); }
+
+/* VirtualEnv.step (envs/virtual_env.py:43-54): input = cat(one_hot(action), state); three nets. */
+void le_oracle_se_step(const le_lane_cfg* c, const float* theta, const float* state, int action, float* next_state,
+                       float* reward, float* done) {
+    int in = c->sd + c->ad, H = c->env_hidden;
+    float x[LE_ORACLE_MAX_IN];
+    for (int a = 0; a < c->ad; ++a) x[a] = (a == action) ? 1.f : 0.f; /* utils.py:108-126 */
+    for (int i = 0; i < c->sd; ++i) x[c->ad + i] = state[i];
+    const float* th_s = theta;
+    const float* th_r = th_s + le_oracle_mlp_params(in, H, c->sd);
+    const float* th_d = th_r + le_oracle_mlp_params(in, H, 1);
+    mlp_forward(th_s, in, H, c->sd, c->env_act, c->env_slope[0], x, next_state, NULL, NULL);
+    mlp_forward(th_r, in, H, 1, c->env_act, c->env_slope[1], x, reward, NULL, NULL);
+    mlp_forward(th_d, in, H, 1, c->env_act, c->env_slope[2], x, done, NULL, NULL);
+}
+
+/* RewardEnv._calc_reward (envs/reward_env.py:68-133), state-only types. Returns <0 for info-vector types
+ * (the reference raises ValueError('No info dict…') for CartPole/Acrobot, envs/reward_env.py:91-92). */
+int le_oracle_rn_reward(const le_lane_cfg* c, const float* theta, const float* s, const float* s2, float real_reward,
+                        float* out) {
+    float ps = 0.f, ps2 = 0.f;
+    float g = (float)c->gamma;
+    int H = c->env_hidden;
+    switch (c->rn_type) {
+        case 0: *out = real_reward; return 0;
+        case 1:
+        case 2:
+            mlp_forward(theta, c->sd, H, 1, c->env_act, c->env_slope[0], s2, &ps2, NULL, NULL);
+            mlp_forward(theta, c->sd, H, 1, c->env_act, c->env_slope[0], s, &ps, NULL, NULL);
+            if (c->rn_type == 1) *out = g * ps2 - ps;
+            else *out = real_reward + g * ps2 - ps; /* (r + γΦ(s')) − Φ(s) */
+            return 0;
+        case 5:
+        case 6:
+            mlp_forward(theta, c->sd, H, 1, c->env_act, c->env_slope[0], s2, &ps2, NULL, NULL);
+            *out = (c->rn_type == 5) ? ps2 : real_reward + ps2;
+            return 0;
+        default: return -1;
+    }
+}
+
+void le_oracle_q_forward(const le_lane_cfg* c, const float* q_theta, const float* state, float* q, int* argmax) {
+    mlp_forward(q_theta, c->sd, c->q_hidden, c->ad, c->q_act, 0.f, state, q, NULL, NULL);
+    int best = 0;
+    for (int a = 1; a < c->ad; ++a)
+        if (q[a] > q[best]) best = a; /* torch.argmax: first maximal index */
+    if (argmax) *argmax = best;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* gym 0.17.3 classic_control (third-party, restated)                             */
+
+void le_oracle_cartpole_step(double st[4], int action, double* reward, int* done) {
+    const double gravity = 9.8, masscart = 1.0, masspole = 0.1;
+    const double total_mass = masspole + masscart;
+    const double length = 0.5;
+    const double polemass_length = masspole * length;
+    const double force_mag = 10.0, tau = 0.02;
+    const double theta_thr = 12 * 2 * M_PI / 360, x_thr = 2.4;
+    double x = st[0], x_dot = st[1], theta = st[2], theta_dot = st[3];
+    double force = action == 1 ? force_mag : -force_mag;
+    double costheta = cos(theta), sintheta = sin(theta);
+    double temp = (force + polemass_length * (theta_dot * theta_dot) * sintheta) / total_mass;
+    double thetaacc = (gravity * sintheta - costheta * temp) /
+                      (length * (4.0 / 3.0 - masspole * (costheta * costheta) / total_mass));
+    double xacc = temp - polemass_length * thetaacc * costheta / total_mass;
+    x = x + tau * x_dot;
+    x_dot = x_dot + tau * xacc;
+    theta = theta + tau * theta_dot;
+    theta_dot = theta_dot + tau * thetaacc;
+    st[0] = x; st[1] = x_dot; st[2] = theta; st[3] = theta_dot;
+    *done = (x < -x_thr || x > x_thr || theta < -theta_thr || theta > theta_thr);
+    *reward = 1.0; /* the agent loop never steps past done (agents/base_agent.py:128) */
+}
+
+static void acrobot_dsdt(const double s[5], double d[5]) {
+    const double m1 = 1., m2 = 1., l1 = 1., lc1 = 0.5, lc2 = 0.5, I1 = 1., I2 = 1., g = 9.8, pi = M_PI;
+    double a = s[4], theta1 = s[0], theta2 = s[1], dtheta1 = s[2], dtheta2 = s[3];
+    double d1 = m1 * (lc1 * lc1) + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * cos(theta2)) + I1 + I2;
+    double d2 = m2 * (lc2 * lc2 + l1 * lc2 * cos(theta2)) + I2;
+    double phi2 = m2 * lc2 * g * cos(theta1 + theta2 - pi / 2.);
+    double phi1 = -m2 * l1 * lc2 * (dtheta2 * dtheta2) * sin(theta2) - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin(theta2) +
+                  (m1 * lc1 + m2 * l1) * g * cos(theta1 - pi / 2) + phi2;
+    double ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * (dtheta1 * dtheta1) * sin(theta2) - phi2) /
+                      (m2 * (lc2 * lc2) + I2 - (d2 * d2) / d1);
+    double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
+    d[0] = dtheta1; d[1] = dtheta2; d[2] = ddtheta1; d[3] = ddtheta2; d[4] = 0.;
+}
+
+static double wrap_pi(double x) {
+    const double m = -M_PI, M = M_PI, diff = M - m;
+    while (x > M) x = x - diff;
+    while (x < m) x = x + diff;
+    return x;
+}
+
+void le_oracle_acrobot_step(double st[4], int action, double* reward, int* done) {
+    const double dt = .2, dt2 = dt / 2.0;
+    double y0[5] = {st[0], st[1], st[2], st[3], (double)(action - 1)}; /* AVAIL_TORQUE = [-1, 0, +1] */
+    double k1[5], k2[5], k3[5], k4[5], y[5];
+    acrobot_dsdt(y0, k1);
+    for (int i = 0; i < 5; ++i) y[i] = y0[i] + dt2 * k1[i];
+    acrobot_dsdt(y, k2);
+    for (int i = 0; i < 5; ++i) y[i] = y0[i] + dt2 * k2[i];
+    acrobot_dsdt(y, k3);
+    for (int i = 0; i < 5; ++i) y[i] = y0[i] + dt * k3[i];
+    acrobot_dsdt(y, k4);
+    for (int i = 0; i < 4; ++i) y[i] = y0[i] + dt / 6.0 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    y[0] = wrap_pi(y[0]);
+    y[1] = wrap_pi(y[1]);
+    const double v1 = 4 * M_PI, v2 = 9 * M_PI;
+    y[2] = fmin(fmax(y[2], -v1), v1);
+    y[3] = fmin(fmax(y[3], -v2), v2);
+    for (int i = 0; i < 4; ++i) st[i] = y[i];
+    int terminal = (-cos(st[0]) - cos(st[1] + st[0]) > 1.);
+    *done = terminal;
+    *reward = terminal ? 0. : -1.;
+}
+
+void le_oracle_real_obs(int real_env, const double st[4], float* obs) {
+    if (real_env == LE_REAL_CARTPOLE) {
+        for (int i = 0; i < 4; ++i) obs[i] = (float)st[i];
+    } else {
+        obs[0] = (float)cos(st[0]); obs[1] = (float)sin(st[0]);
+        obs[2] = (float)cos(st[1]); obs[3] = (float)sin(st[1]);
+        obs[4] = (float)st[2]; obs[5] = (float)st[3];
+    }
+}
+
+/* gym step + TimeLimit (elapsed counted by the caller) */
+void le_oracle_real_step(int real_env, int max_steps, double st[4], int* elapsed, int action, float* obs, float* reward,
+                         float* done) {
+    double r; int d;
+    if (real_env == LE_REAL_CARTPOLE) le_oracle_cartpole_step(st, action, &r, &d);
+    else le_oracle_acrobot_step(st, action, &r, &d);
+    *elapsed += 1;
+    if (*elapsed >= max_steps) d = 1; /* gym/wrappers/time_limit.py */
+    le_oracle_real_obs(real_env, st, obs);
+    *reward = (float)r; /* envs/env_wrapper.py:63-65: torch.tensor(..., dtype=float32) */
+    *done = d ? 1.f : 0.f;
+}
+
+static void real_reset(int real_env, const uint32_t w[4], double st[4]) {
+    double half = real_env == LE_REAL_CARTPOLE ? 0.05 : 0.1;
+    for (int i = 0; i < 4; ++i) st[i] = -half + (half - (-half)) * ((double)w[i] * (1.0 / 4294967296.0));
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* DDQN.learn (agents/DDQN.py:60-95) on an explicit minibatch of packed rows [s a s' r d]               */
+
+float le_oracle_td_update(const le_lane_cfg* c, float* th, float* thT, float* m, float* v, int32_t* adam_t,
+                          const float* rows, int B) {
+    const int sd = c->sd, ad = c->ad, H = c->q_hidden, act = c->q_act;
+    const int P = le_oracle_q_params(c);
+    const int ROW = 2 * sd + 3;
+    float* W1 = th; float* b1 = W1 + H * sd; float* W2 = b1 + H; float* b2 = W2 + ad * H;
+    float* g = (float*)calloc((size_t)P, sizeof(float));
+    float* gW1 = g; float* gb1 = gW1 + H * sd; float* gW2 = gb1 + H; float* gb2 = gW2 + ad * H;
+    float* h = (float*)malloc(sizeof(float) * H * 2);
+    float* z = h + H;
+    float q[LE_ORACLE_MAX_AD], q2[LE_ORACLE_MAX_AD], qT[LE_ORACLE_MAX_AD];
+    const float gam = (float)c->gamma;
+    const float norm = (float)(2.0 / (double)B); /* mse_loss backward, reduction='mean' */
+    double loss_acc = 0.0;
+    float loss_f = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float* r = rows + (size_t)b * ROW;
+        const float* s = r; int a = (int)r[sd]; const float* s2 = r + sd + 1; float rew = r[2 * sd + 1], dn = r[2 * sd + 2];
+        mlp_forward(th, sd, H, ad, act, 0.f, s, q, h, z);          /* q_values = model(states)            :79 */
+        int astar;
+        le_oracle_q_forward(c, th, s2, q2, &astar);               /* next_q_values.max(1)[1]             :80,84 */
+        mlp_forward(thT, sd, H, ad, act, 0.f, s2, qT, NULL, NULL); /* model_target(next_states)           :81 */
+        float y = rew + gam * qT[astar] * (1.f - dn);             /* expected_q_value                    :85 */
+        float delta = q[a] - y;
+        loss_f += delta * delta;
+        loss_acc += (double)delta * delta;
+        float dq = norm * delta;
+        gb2[a] += dq;
+        for (int j = 0; j < H; ++j) {
+            gW2[a * H + j] += dq * h[j];
+            float dz = dq * W2[a * H + j] * act_grad(act, 0.f, z[j], h[j]);
+            gb1[j] += dz;
+            for (int i = 0; i < sd; ++i) gW1[j * sd + i] += dz * s[i];
+        }
+    }
+    (void)loss_acc;
+    float loss = loss_f / (float)B;
+    /* torch.optim.Adam single-tensor step (torch/optim/adam.py _single_tensor_adam), defaults */
+    *adam_t += 1;
+    const double b1d = c->beta1, b2d = c->beta2;
+    const float w1 = (float)(1.0 - b1d), b2f = (float)b2d, w2 = (float)(1.0 - b2d);
+    const double bc1 = 1.0 - pow(b1d, (double)*adam_t), bc2 = 1.0 - pow(b2d, (double)*adam_t);
+    const float neg_step = (float)(-(c->lr / bc1));
+    const float bc2s = (float)sqrt(bc2);
+    const float epsf = (float)c->adam_eps;
+    for (int p = 0; p < P; ++p) {
+        m[p] = m[p] + w1 * (g[p] - m[p]);   /* exp_avg.lerp_(grad, 1-beta1) */
+        v[p] = v[p] * b2f;                  /* exp_avg_sq.mul_(beta2)       */
+        v[p] = v[p] + w2 * g[p] * g[p];     /* .addcmul_(grad, grad, value=1-beta2) */
+        float denom = sqrtf(v[p]) / bc2s + epsf;
+        th[p] = th[p] + neg_step * m[p] / denom; /* param.addcdiv_(exp_avg, denom, value=-step_size) */
+    }
+    /* Polyak (agents/DDQN.py:93-94) */
+    const float tau = (float)c->tau, omt = (float)(1.0 - c->tau);
+    for (int p = 0; p < P; ++p) thT[p] = tau * th[p] + omt * thT[p];
+    (void)b1; (void)b2;
+    free(g); free(h);
+    return loss;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* the lane: BaseAgent.train / test (agents/base_agent.py:64-227) + calc_score (agents/GTN_worker.py:187-221) */
+
+typedef struct {
+    const le_lane_cfg* c;
+    const float* env_theta;
+    uint32_t k0, k1;
+    float* th; float* thT; float* m; float* v; int32_t adam_t;
+    float* rb; int rb_cap; int rb_ptr; int rb_size; /* utils.py:9-32 */
+    int64_t train_steps, learn_iters, test_steps;
+    int test_calls;
+} lane_t;
+
+static double mean_window(const double* vals, int len, int num, int ignore_last) {
+    /* AverageMeter._mean (utils.py:103-105) */
+    int lo = len - num - ignore_last; if (lo < 0) lo = 0;
+    int hi = len - ignore_last; if (hi < 0) hi = 0;
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) s += vals[i];
+    return s / ((double)(hi - lo) + 1e-9);
+}
+
+/* BaseAgent.test (agents/base_agent.py:155-227): greedy rollouts on the real env. */
+static void lane_test(lane_t* L, double* rewards_out) {
+    const le_lane_cfg* c = L->c;
+    for (int ep = 0; ep < c->test_episodes; ++ep) {
+        uint32_t w[4];
+        le_oracle_philox((uint32_t)L->test_calls, (uint32_t)ep, LE_P_RESET_TEST, 0, L->k0, L->k1, w);
+        double st[4]; real_reset(c->real_env, w, st);
+        float obs[LE_ORACLE_MAX_SD]; le_oracle_real_obs(c->real_env, st, obs);
+        int elapsed = 0; float ep_rew = 0.f;
+        for (int t = 0; t < c->max_steps; ++t) {
+            float q[LE_ORACLE_MAX_AD]; int a;
+            le_oracle_q_forward(c, L->th, obs, q, &a);     /* select_test_action agents/DDQN.py:106-110 */
+            float r, d;
+            le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, obs, &r, &d);
+            ep_rew += r; L->test_steps++;
+            if (d > 0.5f) break;
+        }
+        rewards_out[ep] = (double)ep_rew;
+    }
+    L->test_calls++;
+}
+
+int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0, uint32_t k1, const float* q_init,
+                       float* q_final, le_lane_out* out, double* rewards, int32_t* lengths, double* test_rewards,
+                       const le_trace* tr) {
+    if (c->sd > LE_ORACLE_MAX_SD || c->ad > LE_ORACLE_MAX_AD) return -1;
+    const int sd = c->sd, ad = c->ad, P = le_oracle_q_params(c), ROW = 2 * sd + 3;
+    lane_t L; memset(&L, 0, sizeof(L));
+    L.c = c; L.env_theta = env_theta; L.k0 = k0; L.k1 = k1;
+    L.th = (float*)malloc(sizeof(float) * P * 4);
+    L.thT = L.th + P; L.m = L.thT + P; L.v = L.m + P;
+    if (q_init) memcpy(L.th, q_init, sizeof(float) * P);
+    else le_oracle_q_init(c, k0, k1, L.th);
+    memcpy(L.thT, L.th, sizeof(float) * P);           /* model_target.load_state_dict  agents/DDQN.py:36 */
+    memset(L.m, 0, sizeof(float) * P * 2);
+    int64_t max_total = (int64_t)c->train_episodes * c->max_steps;
+    if (c->step_budget > 0 && c->step_budget + c->max_steps < max_total) max_total = c->step_budget + c->max_steps;
+    L.rb_cap = c->rb_size < max_total ? c->rb_size : (int)max_total;
+    if (L.rb_cap < 1) L.rb_cap = 1;
+    L.rb = (float*)malloc(sizeof(float) * (size_t)L.rb_cap * ROW);
+    float* batch = (float*)malloc(sizeof(float) * (size_t)c->batch_size * ROW);
+    double* test_tmp = (double*)malloc(sizeof(double) * (c->test_episodes > 0 ? c->test_episodes : 1));
+
+    double eps = c->eps_init;
+    int n_ep = 0, timed_out = 0;
+    const int rule_virtual = (!c->use_test_env && c->env_kind == LE_ENV_SE);
+    for (int episode = 0; episode < c->train_episodes; ++episode) {
+        if (c->step_budget > 0 && L.train_steps >= c->step_budget) { timed_out = 1; break; } /* time_is_up :91-96 */
+        /* update_parameters_per_episode (agents/DDQN.py:112-117) */
+        if (episode == 0) eps = c->eps_init;
+        else { eps *= c->eps_decay; if (eps < c->eps_min) eps = c->eps_min; }
+        /* env.reset(): SE -> reset_env.reset() cast to f32 (envs/virtual_env.py:35-41); RN/REAL -> gym reset */
+        uint32_t w[4];
+        le_oracle_philox((uint32_t)episode, 0, LE_P_RESET_TRAIN, 0, k0, k1, w);
+        double st[4]; real_reset(c->real_env, w, st);
+        float state[LE_ORACLE_MAX_SD]; le_oracle_real_obs(c->real_env, st, state);
+        int elapsed = 0;
+        float ep_rew = 0.f; int ep_len = 0;
+        for (int t = 0; t < c->max_steps; ++t) {
+            /* select_train_action (agents/DDQN.py:97-104) */
+            le_oracle_philox((uint32_t)L.train_steps, 0, LE_P_ACT, 0, k0, k1, w);
+            double u = (double)(w[0] >> 8) * (1.0 / 16777216.0);
+            int a, explore = (u < eps);
+            if (explore) a = (int)mulhi32(w[1], (uint32_t)ad);
+            else { float q[LE_ORACLE_MAX_AD]; le_oracle_q_forward(c, L.th, state, q, &a); }
+            /* env.step */
+            float ns[LE_ORACLE_MAX_SD], r, d;
+            if (c->env_kind == LE_ENV_SE) {
+                le_oracle_se_step(c, env_theta, state, a, ns, &r, &d);
+            } else {
+                float rr;
+                le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, ns, &rr, &d);
+                if (c->env_kind == LE_ENV_RN) {
+                    /* RewardEnv.step: state/next_state are the fp64 gym states cast to f32 (:78-79) */
+                    if (le_oracle_rn_reward(c, env_theta, state, ns, rr, &r) != 0) { free(L.th); free(L.rb); free(batch); free(test_tmp); return -2; }
+                } else r = rr;
+            }
+            /* replay_buffer.add (utils.py:24-32) */
+            float* row = L.rb + (size_t)L.rb_ptr * ROW;
+            memcpy(row, state, sizeof(float) * sd); row[sd] = (float)a; memcpy(row + sd + 1, ns, sizeof(float) * sd);
+            row[2 * sd + 1] = r; row[2 * sd + 2] = d;
+            L.rb_ptr = (L.rb_ptr + 1) % L.rb_cap;
+            L.rb_size = L.rb_size + 1 < L.rb_cap ? L.rb_size + 1 : L.rb_cap;
+            memcpy(state, ns, sizeof(float) * sd);
+            ep_rew += r; ep_len += 1;
+            float loss = NAN;
+            if (episode >= c->init_episodes) { /* learn (agents/DDQN.py:60-95) */
+                for (int b = 0; b < c->batch_size; b += 4) {
+                    le_oracle_philox((uint32_t)L.learn_iters, (uint32_t)(b >> 2), LE_P_SAMPLE, 0, k0, k1, w);
+                    for (int k = 0; k < 4 && b + k < c->batch_size; ++k) {
+                        uint32_t idx = mulhi32(w[k], (uint32_t)L.rb_size); /* np.random.randint(0,size) utils.py:35 */
+                        memcpy(batch + (size_t)(b + k) * ROW, L.rb + (size_t)idx * ROW, sizeof(float) * ROW);
+                    }
+                }
+                loss = le_oracle_td_update(c, L.th, L.thT, L.m, L.v, &L.adam_t, batch, c->batch_size);
+                L.learn_iters++;
+            }
+            if (tr && tr->cap > 0 && L.train_steps < tr->cap) {
+                int64_t i = L.train_steps;
+                tr->action[i] = a; tr->explore[i] = explore; tr->reward[i] = r; tr->done[i] = d; tr->loss[i] = loss;
+                memcpy(tr->next_state + i * sd, ns, sizeof(float) * sd);
+            }
+            L.train_steps++;
+            if (d > 0.5f) break;
+        }
+        lengths[n_ep] = ep_len;
+        if (c->use_test_env) {
+            lane_test(&L, test_tmp);
+            double s = 0.0; for (int i = 0; i < c->test_episodes; ++i) s += test_tmp[i];
+            rewards[n_ep] = s / (double)c->test_episodes; /* statistics.mean */
+        } else rewards[n_ep] = (double)ep_rew;
+        n_ep++;
+        if (episode >= c->init_episodes) { /* env_solved (agents/base_agent.py:49-62) */
+            double avg = mean_window(rewards, n_ep, c->early_out_num, 0);
+            double avg_last = mean_window(rewards, n_ep, c->early_out_num, c->early_out_num);
+            int solved;
+            if (rule_virtual)
+                solved = (fabs(avg - avg_last) / (fabs(avg_last) + 1e-9) < c->early_out_virtual_diff) &&
+                         (episode >= c->init_episodes + c->early_out_num);
+            else solved = (avg >= c->solved_reward);
+            if (solved) break;
+        }
+    }
+    double score = 0.0;
+    if (c->final_test) {
+        lane_test(&L, test_rewards);
+        for (int i = 0; i < c->test_episodes; ++i) score += test_rewards[i];
+        score /= (double)c->test_episodes;
+    }
+    out->n_episodes = n_ep; out->timed_out = timed_out; out->train_steps = L.train_steps;
+    out->learn_iters = L.learn_iters; out->test_steps = L.test_steps; out->score = score;
+    if (q_final) memcpy(q_final, L.th, sizeof(float) * P);
+    free(L.th); free(L.rb); free(batch); free(test_tmp);
+    return 0;
+}
+
+/* torch default nn.Linear init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias, drawn from the
+ * P_QINIT stream in canonical parameter order (distribution of models/model_utils.py:31,38; the stream is ours). */
+void le_oracle_q_init(const le_lane_cfg* c, uint32_t k0, uint32_t k1, float* th) {
+    const int sd = c->sd, H = c->q_hidden, P = le_oracle_q_params(c);
+    const int n1 = H * sd + H;
+    const double bnd1 = 1.0 / sqrt((double)sd), bnd2 = 1.0 / sqrt((double)H);
+    for (int p = 0; p < P; p += 4) {
+        uint32_t w[4];
+        le_oracle_philox((uint32_t)(p >> 2), 0, LE_P_QINIT, 0, k0, k1, w);
+        for (int k = 0; k < 4 && p + k < P; ++k) {
+            double u = ((double)w[k] + 0.5) * (1.0 / 4294967296.0);
+            th[p + k] = (float)((2.0 * u - 1.0) * ((p + k) < n1 ? bnd1 : bnd2));
+        }
+    }
+}
+
+/* n independent lanes on n_threads pthreads (dynamic lane queue).  The reference runs one single-threaded
+ * process per member (experiments/GTN_Worker.py:8).  cfgs: n_cfg == 1 shares the configuration. */
+typedef struct {
+    const le_lane_cfg* cfgs; int n_cfg; const float* env_theta; int P_env; const int32_t* env_index;
+    const uint32_t* keys; const float* q_init; float* q_final; int n_lanes; le_lane_out* out;
+    double* rewards; int32_t* lengths; double* test_rewards;
+    int next; int rc; pthread_mutex_t mu;
+} lanes_job_t;
+
+static void* lanes_worker(void* arg) {
+    lanes_job_t* J = (lanes_job_t*)arg;
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        int i = J->next++;
+        pthread_mutex_unlock(&J->mu);
+        if (i >= J->n_lanes) break;
+        const le_lane_cfg* c = &J->cfgs[J->n_cfg == 1 ? 0 : i];
+        const le_lane_cfg* c0 = &J->cfgs[0];
+        int Pq = le_oracle_q_params(c0); /* strides follow cfg 0 (max shapes) */
+        const float* th = J->env_theta + (size_t)(J->env_index ? J->env_index[i] : 0) * J->P_env;
+        int r = le_oracle_run_lane(c, th, J->keys[2 * i], J->keys[2 * i + 1], J->q_init ? J->q_init + (size_t)i * Pq : NULL,
+                                   J->q_final ? J->q_final + (size_t)i * Pq : NULL, &J->out[i],
+                                   J->rewards + (size_t)i * c0->train_episodes, J->lengths + (size_t)i * c0->train_episodes,
+                                   J->test_rewards + (size_t)i * c0->test_episodes, NULL);
+        if (r != 0) { pthread_mutex_lock(&J->mu); J->rc = r; pthread_mutex_unlock(&J->mu); }
+    }
+    return NULL;
+}
+
+int le_oracle_run_lanes(const le_lane_cfg* cfgs, int n_cfg, const float* env_theta, int P_env, const int32_t* env_index,
+                        const uint32_t* keys, const float* q_init, float* q_final, int n_lanes, le_lane_out* out,
+                        double* rewards, int32_t* lengths, double* test_rewards, int n_threads) {
+    lanes_job_t J = {cfgs, n_cfg, env_theta, P_env, env_index, keys, q_init, q_final, n_lanes, out,
+                     rewards, lengths, test_rewards, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t tid[256];
+    for (int t = 1; t < n_threads; ++t) pthread_create(&tid[t], NULL, lanes_worker, &J);
+    lanes_worker(&J);
+    for (int t = 1; t < n_threads; ++t) pthread_join(tid[t], NULL);
+    return J.rc;
+}
+
+int le_oracle_sizeof_cfg(void) { return (int)sizeof(le_lane_cfg); }

@@ -1,0 +1,45 @@
+/* le_oracle.h — TEST INFRASTRUCTURE ONLY: prototypes of the CPU restatement (see le_oracle.c). */
+#ifndef LE_ORACLE_H
+#define LE_ORACLE_H
+#include <stdint.h>
+
+#include "../include/le_b200.h" /* le_lane_cfg, le_lane_out, le_trace, LE_* ids */
+
+#define LE_ORACLE_MAX_SD 8
+#define LE_ORACLE_MAX_AD 4
+#define LE_ORACLE_MAX_IN (LE_ORACLE_MAX_SD + LE_ORACLE_MAX_AD)
+
+/* Philox stream purposes (oracle/philox.py) */
+#define LE_P_ACT 1
+#define LE_P_SAMPLE 2
+#define LE_P_RESET_TRAIN 3
+#define LE_P_RESET_TEST 4
+#define LE_P_QINIT 5
+#define LE_P_NOISE 6
+
+void le_oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]);
+int le_oracle_mlp_params(int in, int H, int out);
+int le_oracle_se_params(const le_lane_cfg* c);
+int le_oracle_rn_params(const le_lane_cfg* c);
+int le_oracle_q_params(const le_lane_cfg* c);
+void le_oracle_se_step(const le_lane_cfg* c, const float* theta, const float* state, int action, float* next_state,
+                       float* reward, float* done);
+int le_oracle_rn_reward(const le_lane_cfg* c, const float* theta, const float* s, const float* s2, float real_reward,
+                        float* out);
+void le_oracle_q_forward(const le_lane_cfg* c, const float* q_theta, const float* state, float* q, int* argmax);
+void le_oracle_cartpole_step(double st[4], int action, double* reward, int* done);
+void le_oracle_acrobot_step(double st[4], int action, double* reward, int* done);
+void le_oracle_real_obs(int real_env, const double st[4], float* obs);
+void le_oracle_real_step(int real_env, int max_steps, double st[4], int* elapsed, int action, float* obs, float* reward,
+                         float* done);
+float le_oracle_td_update(const le_lane_cfg* c, float* th, float* thT, float* m, float* v, int32_t* adam_t,
+                          const float* rows, int B);
+void le_oracle_q_init(const le_lane_cfg* c, uint32_t k0, uint32_t k1, float* th);
+int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0, uint32_t k1, const float* q_init,
+                       float* q_final, le_lane_out* out, double* rewards, int32_t* lengths, double* test_rewards,
+                       const le_trace* tr);
+int le_oracle_run_lanes(const le_lane_cfg* cfgs, int n_cfg, const float* env_theta, int P_env, const int32_t* env_index,
+                        const uint32_t* keys, const float* q_init, float* q_final, int n_lanes, le_lane_out* out,
+                        double* rewards, int32_t* lengths, double* test_rewards, int n_threads);
+int le_oracle_sizeof_cfg(void);
+#endif
