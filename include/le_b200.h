@@ -112,8 +112,13 @@ typedef struct le_trace {
 /* library                                                                                          */
 int le_version(void);
 const char* le_last_error(void);
+int le_sizeof_lane_cfg(void); /* ABI check for bindings */
 /* number of SMs / name of the current device (diagnostics for bench.py) */
 int le_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_cap);
+
+/* Measured FP32 FFMA throughput of the current device in TFLOP/s (microbenchmark; the roofline denominator
+ * of the FFMA-bound fused kernel — MEASURED_PEAKS.json carries only HBM and bf16-tensor peaks). */
+int le_bench_ffma(int iters, int reps, double* tflops_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* unit operators (one reference call each), batched over `n` independent rows/lanes                 */
@@ -149,8 +154,14 @@ int le_td_update(const le_lane_cfg* cfg, float* q_theta_dev, float* q_target_dev
 /* ------------------------------------------------------------------------------------------------ */
 /* the fused hot path                                                                               */
 
-/* Bytes of device workspace needed for n lanes (replay rings, per-lane scratch). */
-int64_t le_inner_loop_workspace_bytes(const le_lane_cfg* cfg, int n_lanes, int trace_cap);
+/* Bytes of device workspace needed for n lanes sharing n_env environment parameter vectors: the packed
+ * SE/RN weights, one replay ring per RESIDENT warp slot (not per lane) and the lane queue counter.
+ * Returns a negative LE_E* code on error. */
+int64_t le_inner_loop_workspace_bytes(const le_lane_cfg* cfg, int n_lanes, int n_env);
+
+/* The launch plan behind the two calls above/below (diagnostics for bench.py / DESIGN.md): CTAs, resident
+ * warp slots, replay ring capacity in rows, hidden units per thread of the selected kernel set. */
+int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid, int* slots, int* ring_cap, int* units);
 
 /*
  * Runs n_lanes complete `calc_score`s (agents/GTN_worker.py:187-221) — train() with ε-greedy acting
@@ -158,8 +169,9 @@ int64_t le_inner_loop_workspace_bytes(const le_lane_cfg* cfg, int n_lanes, int t
  * (agents/DDQN.py:60-95), per-episode greedy test() on the real env, early-out (agents/base_agent.py:49-62)
  * and the final test() — in ONE persistent kernel, one warp per lane.
  *
- *   cfg_dev        [n_cfg] lane configurations; lane i uses cfg_dev[n_cfg == 1 ? 0 : i]  (vary_hp: per-lane
- *                  lr / batch_size / q_hidden)
+ *   cfg_dev        [n_cfg] lane configurations (DEVICE); lane i uses cfg_dev[n_cfg == 1 ? 0 : i]  (vary_hp:
+ *                  per-lane lr / batch_size / q_hidden <= cfg_host0->q_hidden).  cfg_host0 = HOST copy of the
+ *                  configuration that fixes shapes, strides and the ring capacity (cfg 0 / the maxima)
  *   env_theta_dev  [n_env][P_env]; lane i uses row env_index_dev[i] (NULL: row 0)
  *   keys_dev       [n_lanes][2] Philox lane keys
  *   q_init_dev     NULL: Q-nets are initialised on device from the P_QINIT stream (torch default init
@@ -173,7 +185,7 @@ int64_t le_inner_loop_workspace_bytes(const le_lane_cfg* cfg, int n_lanes, int t
  *   trace_dev      NULL or one le_trace (device pointers inside) that records lane `trace_lane`
  */
 int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* cfg_host0,
-                      const float* env_theta_dev, const int32_t* env_index_dev, const uint32_t* keys_dev,
+                      const float* env_theta_dev, int n_env, const int32_t* env_index_dev, const uint32_t* keys_dev,
                       const float* q_init_dev, float* q_final_dev, int n_lanes, le_lane_out* out_dev,
                       double* rewards_dev, int32_t* lengths_dev, double* test_rewards_dev, void* workspace_dev,
                       int64_t workspace_bytes, const le_trace* trace_host, int trace_lane, void* stream);
@@ -201,7 +213,7 @@ int le_nes_noise(int P, int member_offset, int n_members, uint32_t seed, uint32_
 /* update_env: theta <- theta*(1-wd); for i in 0..pop-1 (in order): theta += coef[i]*sign[i]*eps_i, with
  * eps_i regenerated from Philox; coef[i] = (float)(step_size * score_transform[i]).                   */
 int le_nes_update(float* theta_dev /*[P]*/, int P, int pop, uint32_t seed, uint32_t generation,
-                  float noise_std, float weight_decay, const float* coef_dev /*[pop]*/,
+                  float noise_std, double weight_decay, const float* coef_dev /*[pop]*/,
                   const float* sign_dev /*[pop] +1/-1*/, void* stream);
 
 /* Partial (sharded) form for the allreduce path: delta[P] = sum_{i in [lo,hi)} coef[i]*sign[i]*eps_i.    */

@@ -101,9 +101,9 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "le_version", "le_last_error", "le_device_info",
+    "le_version", "le_last_error", "le_sizeof_lane_cfg", "le_device_info", "le_bench_ffma",
     "le_se_forward", "le_rn_reward", "le_qnet_forward", "le_real_env_step", "le_td_update",
-    "le_inner_loop_workspace_bytes", "le_inner_loop_run", "le_inner_loop_run_host",
+    "le_inner_loop_workspace_bytes", "le_inner_loop_plan", "le_inner_loop_run", "le_inner_loop_run_host",
     "le_nes_perturb", "le_nes_noise", "le_nes_update", "le_nes_partial_update",
 ]
 

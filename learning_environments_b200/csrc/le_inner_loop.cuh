@@ -1,0 +1,297 @@
+// le_inner_loop.cuh — the persistent fused kernel: one warp runs one lane's complete calc_score
+// (agents/GTN_worker.py:187-221): BaseAgent.train (agents/base_agent.py:64-153) with eps-greedy acting
+// (agents/DDQN.py:97-104), SE / RN / real env step, replay append (utils.py:24-32), DDQN.learn
+// (agents/DDQN.py:60-95), per-episode greedy test() on the real env (agents/base_agent.py:155-227), the
+// early-out rule (agents/base_agent.py:49-62) and the final test().  Warps pull lanes from a global queue.
+#pragma once
+#include "le_envpack.cuh"
+#include "le_lane.cuh"
+
+namespace le {
+
+struct RunParams {
+    const le_lane_cfg* cfg; int n_cfg;
+    const float4* env_pack; int64_t env_pack_stride;  // in float4
+    const int32_t* env_index;
+    const uint32_t* keys;
+    const float* q_init; float* q_final; int q_stride;
+    int n_lanes;
+    le_lane_out* out;
+    double* rewards; int32_t* lengths; double* test_rewards;
+    int rew_stride, test_stride;
+    float* rings; int64_t ring_stride; int ring_cap;  // one replay ring per resident warp slot
+    int* work_counter;
+    le_trace trace; int trace_lane;
+};
+
+constexpr int kWarpsPerCta = 4;
+
+template <int SD, int AD, int U>
+struct SmemWarp {
+    static constexpr int PUP = ((SD + 1 + AD) + 3) / 4 * 4;  // padded per-unit record of the test-phase weight image
+    static constexpr int STAGE_F = kStageRows * RowLayout<SD>::ROWF;
+    static constexpr int QW_F = U * 32 * PUP;
+    static constexpr int FLOATS = STAGE_F > QW_F ? STAGE_F : QW_F;
+};
+
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) { return __ldcg(p); }
+
+// AverageMeter._mean (utils.py:103-105) over the per-lane reward list in global memory
+__device__ __forceinline__ double mean_window(const double* vals, int len, int num, int ignore_last) {
+    int lo = len - num - ignore_last; if (lo < 0) lo = 0;
+    int hi = len - ignore_last; if (hi < 0) hi = 0;
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) s += vals[i];
+    return s / ((double)(hi - lo) + 1e-9);
+}
+
+template <int SD, int AD, int U, int ACT>
+struct FusedLane {
+    using Core = LaneCore<SD, AD, U, ACT>;
+    using RL = RowLayout<SD>;
+    using SW = SmemWarp<SD, AD, U>;
+
+    // BaseAgent.test: greedy rollouts on the real env, one episode per thread, weights broadcast from smem.
+    static __device__ __forceinline__ double run_test(const Core& core, float* smem, const le_lane_cfg& c, float slope,
+                                                      uint32_t k0, uint32_t k1, int test_call, int lane,
+                                                      double* ep_out /* [test_episodes] or nullptr */, int64_t& test_steps) {
+        constexpr int PUP = SW::PUP;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float* rec = smem + (lane + 32 * u) * PUP;
+#pragma unroll
+            for (int i = 0; i < SD; ++i) rec[i] = core.w1[u][i];
+            rec[SD] = core.b1[u];
+#pragma unroll
+            for (int a = 0; a < AD; ++a) rec[SD + 1 + a] = core.w2[u][a];
+        }
+        __syncwarp();
+        const int H = c.q_hidden;
+        double sum = 0.0;
+        int steps = 0;
+        for (int ep0 = 0; ep0 < c.test_episodes; ep0 += 32) {
+            const int ep = ep0 + lane;
+            const bool active = ep < c.test_episodes;
+            double st[4];
+            real_reset(c.real_env, philox4x32_10((uint32_t)test_call, (uint32_t)ep, LE_P_RESET_TEST, 0u, k0, k1), st);
+            float obs[SD];
+            real_obs<SD>(c.real_env, st, obs);
+            int elapsed = 0;
+            float ep_rew = 0.f;
+            bool running = active;
+            for (int t = 0; t < c.max_steps; ++t) {
+                if (!__any_sync(LE_FULL_MASK, running)) break;
+                if (running) {
+                    float q[AD];
+#pragma unroll
+                    for (int a = 0; a < AD; ++a) q[a] = 0.f;
+                    for (int j = 0; j < H; ++j) {
+                        const float* rec = smem + j * PUP;
+                        float z = rec[SD];
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) z = fmaf(rec[i], obs[i], z);
+                        const float h = q_act<ACT>(z, slope);
+#pragma unroll
+                        for (int a = 0; a < AD; ++a) q[a] = fmaf(h, rec[SD + 1 + a], q[a]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < AD; ++a) q[a] += core.b2[a];
+                    const int act = Core::argmax_first(q);  // select_test_action agents/DDQN.py:106-110
+                    float r, d;
+                    real_step<SD>(c.real_env, c.max_steps, st, elapsed, act, obs, r, d);
+                    ep_rew += r;
+                    steps += 1;
+                    if (d > 0.5f) running = false;
+                }
+            }
+            if (active) {
+                sum += (double)ep_rew;
+                if (ep_out) ep_out[ep] = (double)ep_rew;
+            }
+        }
+        sum = warp_allreduce_sum(sum);
+        int tot = steps;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) tot += __shfl_xor_sync(LE_FULL_MASK, tot, m);
+        test_steps += tot;
+        __syncwarp();
+        return sum / (double)c.test_episodes;  // statistics.mean
+    }
+
+    static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane) {
+        const le_lane_cfg c = P.cfg[P.n_cfg == 1 ? 0 : lane_id];
+        const uint32_t k0 = P.keys[2 * lane_id], k1 = P.keys[2 * lane_id + 1];
+        const float4* pack = P.env_pack + (int64_t)(P.env_index ? P.env_index[lane_id] : 0) * P.env_pack_stride;
+        const bool env_tanh = c.env_act == LE_ACT_TANH;
+        const int H = c.q_hidden;
+        float* ring = P.rings + (int64_t)slot * P.ring_stride;
+        const int ring_cap = P.ring_cap;
+        double* rewards = P.rewards + (int64_t)lane_id * P.rew_stride;
+        int32_t* lengths = P.lengths + (int64_t)lane_id * P.rew_stride;
+        double* test_rewards = P.test_rewards + (int64_t)lane_id * P.test_stride;
+        const bool tracing = P.trace.cap > 0 && lane_id == P.trace_lane;
+
+        Core core;
+        if (P.q_init) core.load_net(P.q_init + (int64_t)lane_id * P.q_stride, H, lane, core.w1, core.b1, core.w2, core.b2);
+        else core.init_online(H, lane, k0, k1);
+        core.copy_online_to_target();  // model_target.load_state_dict(model.state_dict())   agents/DDQN.py:36
+        core.zero_moments();
+        LearnScalars ls;
+        fill_learn_scalars(ls, c);
+
+        int rb_ptr = 0, rb_size = 0;
+        int64_t train_steps = 0, learn_iters = 0, test_steps = 0;
+        int test_calls = 0, n_ep = 0, timed_out = 0;
+        double eps = c.eps_init;
+        const bool rule_virtual = (!c.use_test_env) && c.env_kind == LE_ENV_SE;
+
+        for (int episode = 0; episode < c.train_episodes; ++episode) {
+            if (c.step_budget > 0 && train_steps >= c.step_budget) { timed_out = 1; break; }  // time_is_up analog
+            if (episode == 0) eps = c.eps_init;                                              // agents/DDQN.py:112-117
+            else { eps *= c.eps_decay; if (eps < c.eps_min) eps = c.eps_min; }
+            double st[4];
+            real_reset(c.real_env, philox4x32_10((uint32_t)episode, 0u, LE_P_RESET_TRAIN, 0u, k0, k1), st);
+            float state[SD];
+            real_obs<SD>(c.real_env, st, state);
+            int elapsed = 0, ep_len = 0;
+            float ep_rew = 0.f;
+            for (int t = 0; t < c.max_steps; ++t) {
+                // ---- select_train_action (agents/DDQN.py:97-104)
+                const u32x4 wa = philox4x32_10((uint32_t)train_steps, 0u, LE_P_ACT, 0u, k0, k1);
+                const bool explore = ((double)(wa.x >> 8) * (1.0 / 16777216.0)) < eps;
+                int action;
+                if (explore) action = (int)__umulhi(wa.y, (uint32_t)AD);
+                else {
+                    float q[AD];
+                    core.q_forward_row(state, ls.slope, q);
+                    action = Core::argmax_first(q);
+                }
+                // ---- env.step
+                float ns[SD], r, d;
+                if (c.env_kind == LE_ENV_SE) {
+                    se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, state, action, lane, ns, r, d);
+                } else {
+                    float rr;
+                    real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
+                    if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
+                        float ps, ps2;
+                        rn_phi2<SD>(pack, c.env_hidden, env_tanh, state, ns, lane, ps, ps2);
+                        r = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
+                    } else r = rr;
+                }
+                // ---- replay_buffer.add (utils.py:24-32): row [s a s' r d] in the 16B-aligned layout RL
+                {
+                    float rowv[RL::ROWF];
+#pragma unroll
+                    for (int i = 0; i < RL::ROWF; ++i) rowv[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) { rowv[RL::OFF_S + i] = state[i]; rowv[RL::OFF_S2 + i] = ns[i]; }
+                    rowv[RL::OFF_A] = (float)action; rowv[RL::OFF_R] = r; rowv[RL::OFF_D] = d;
+                    float4* dst = reinterpret_cast<float4*>(ring + (int64_t)rb_ptr * RL::ROWF);
+#pragma unroll
+                    for (int q = 0; q < RL::ROW_VEC; ++q)
+                        if (lane == q) __stcg(dst + q, make_float4(rowv[4 * q], rowv[4 * q + 1], rowv[4 * q + 2], rowv[4 * q + 3]));
+                    rb_ptr = (rb_ptr + 1 == ring_cap) ? 0 : rb_ptr + 1;
+                    rb_size = rb_size + 1 < ring_cap ? rb_size + 1 : ring_cap;
+                }
+#pragma unroll
+                for (int i = 0; i < SD; ++i) state[i] = ns[i];
+                ep_rew += r;
+                ep_len += 1;
+                // ---- learn (agents/DDQN.py:60-95)
+                float loss = __int_as_float(0x7fc00000);
+                if (episode >= c.init_episodes) {
+                    __syncwarp();  // the appended row is visible to the whole warp
+                    core.zero_grads();
+                    float loss_part = 0.f;
+                    const int B = ls.batch;
+                    for (int sc = 0; sc * kStageRows < B; ++sc) {
+                        const int nrows = min(kStageRows, B - sc * kStageRows);
+                        const int nfill = (nrows + Core::R - 1) / Core::R * Core::R;
+                        // replay_buffer.sample: idx = randint(0, size, B) on the P_SAMPLE stream (utils.py:35)
+                        const int blk = sc * 32 + lane;
+                        if (4 * lane < nfill) {
+                            const u32x4 w = philox4x32_10((uint32_t)learn_iters, (uint32_t)blk, LE_P_SAMPLE, 0u, k0, k1);
+                            float4 v[4][RL::ROW_VEC];
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const bool ok = 4 * lane + kk < nrows;
+                                const uint32_t idx = __umulhi(pick(w, kk), (uint32_t)rb_size);
+                                const float4* src = reinterpret_cast<const float4*>(ring + (int64_t)idx * RL::ROWF);
+#pragma unroll
+                                for (int q = 0; q < RL::ROW_VEC; ++q) v[kk][q] = ok ? ld_cg_f4(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                float4* dsts = reinterpret_cast<float4*>(smem + (4 * lane + kk) * RL::ROWF);
+#pragma unroll
+                                for (int q = 0; q < RL::ROW_VEC; ++q) dsts[q] = v[kk][q];
+                            }
+                        }
+                        __syncwarp();
+                        loss_part += core.td_rows(smem, nrows, ls, lane);
+                        __syncwarp();
+                    }
+                    loss = warp_allreduce_sum(loss_part) / (float)B;
+                    core.adam_polyak(ls);
+                    learn_iters += 1;
+                }
+                if (tracing && train_steps < P.trace.cap && lane == 0) {
+                    const int64_t i = train_steps;
+                    P.trace.action[i] = action; P.trace.explore[i] = explore ? 1 : 0;
+                    P.trace.reward[i] = r; P.trace.done[i] = d; P.trace.loss[i] = loss;
+#pragma unroll
+                    for (int k = 0; k < SD; ++k) P.trace.next_state[i * SD + k] = ns[k];
+                }
+                train_steps += 1;
+                if (d > 0.5f) break;
+            }
+            // ---- episode bookkeeping (agents/base_agent.py:131-148)
+            double ep_value;
+            if (c.use_test_env) ep_value = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, nullptr, test_steps);
+            else ep_value = (double)ep_rew;
+            if (lane == 0) { lengths[n_ep] = ep_len; rewards[n_ep] = ep_value; }
+            n_ep += 1;
+            __syncwarp();
+            if (episode >= c.init_episodes) {  // env_solved (agents/base_agent.py:49-62)
+                const double avg = mean_window(rewards, n_ep, c.early_out_num, 0);
+                bool solved;
+                if (rule_virtual) {
+                    const double avg_last = mean_window(rewards, n_ep, c.early_out_num, c.early_out_num);
+                    solved = (fabs(avg - avg_last) / (fabs(avg_last) + 1e-9) < c.early_out_virtual_diff) &&
+                             (episode >= c.init_episodes + c.early_out_num);
+                } else solved = avg >= c.solved_reward;
+                if (solved) break;
+            }
+        }
+        double score = 0.0;
+        if (c.final_test) score = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, test_rewards, test_steps);
+        if (P.q_final) core.store_net(P.q_final + (int64_t)lane_id * P.q_stride, H, lane, core.w1, core.b1, core.w2, core.b2);
+        if (lane == 0) {
+            le_lane_out o;
+            o.n_episodes = n_ep; o.timed_out = timed_out; o.train_steps = train_steps; o.learn_iters = learn_iters;
+            o.test_steps = test_steps; o.score = score;
+            P.out[lane_id] = o;
+        }
+    }
+};
+
+template <int SD, int AD, int U, int ACT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) inner_loop_kernel(const RunParams P) {
+    using SW = SmemWarp<SD, AD, U>;
+    __shared__ __align__(16) float smem_all[kWarpsPerCta][SW::FLOATS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * kWarpsPerCta + warp;
+    float* smem = smem_all[warp];
+    for (;;) {
+        int lane_id = 0;
+        if (lane == 0) lane_id = atomicAdd(P.work_counter, 1);
+        lane_id = __shfl_sync(LE_FULL_MASK, lane_id, 0);
+        if (lane_id >= P.n_lanes) break;
+        FusedLane<SD, AD, U, ACT>::run(P, lane_id, slot, smem, lane);
+        __syncwarp();
+    }
+}
+
+}  // namespace le

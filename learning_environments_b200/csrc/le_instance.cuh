@@ -1,0 +1,217 @@
+// le_instance.cuh — launchers for one compiled (SD, AD, U, ACT) kernel set.  The instantiations live in
+// le_inst_*.cu (one translation unit per environment shape x activation so they compile in parallel);
+// le_api.cu looks them up with le_find_instance().
+#pragma once
+#include "le_inner_loop.cuh"
+
+namespace le {
+
+struct InstanceOps {
+    int sd, ad, units, act;  // act: QACT_TANH / QACT_LEAKY
+    // fused persistent kernel
+    int (*inner_max_ctas_per_sm)();
+    cudaError_t (*launch_inner)(const RunParams& P, int grid, cudaStream_t st);
+    int64_t (*ring_row_floats)();
+    // environment packing
+    int64_t (*se_pack_vec4)(int H);
+    int64_t (*rn_pack_vec4)(int H);
+    cudaError_t (*launch_pack_se)(const float* theta, int P_env, int n_env, int H, const float* slopes, float* out,
+                                  int64_t out_stride_f, cudaStream_t st);
+    cudaError_t (*launch_pack_rn)(const float* theta, int P_env, int n_env, int H, float slope, float* out,
+                                  int64_t out_stride_f, cudaStream_t st);
+    // unit operators
+    cudaError_t (*launch_se_forward)(const float4* pack, int64_t pack_stride, int H, int is_tanh, int lanes_per_member,
+                                     const float* state, const int32_t* action, float* ns, float* reward, float* done, int n,
+                                     cudaStream_t st);
+    cudaError_t (*launch_rn_reward)(const float4* pack, int64_t pack_stride, int H, int is_tanh, int rn_type, float gamma,
+                                    int lanes_per_member, const float* s, const float* s2, const float* rr, float* out, int n,
+                                    cudaStream_t st);
+    cudaError_t (*launch_qnet_forward)(const float* q_theta, int q_stride, int H, float slope, const float* state, float* q_out,
+                                       int32_t* argmax, int n, cudaStream_t st);
+    cudaError_t (*launch_td_update)(const le_lane_cfg* cfg_dev, float* th, float* thT, float* m, float* v, int32_t* t, int q_stride,
+                                    const float* rows, int B, float* loss, int n, cudaStream_t st);
+};
+
+const InstanceOps* le_find_instance(int sd, int ad, int units_needed, int act);
+void le_register_instance(const InstanceOps* ops);
+
+// ------------------------------------------------------------------------------------------------------
+// unit kernels (one warp per row / lane), sharing the device code of the fused kernel
+
+template <int SD, int AD>
+__global__ void se_forward_kernel(const float4* __restrict__ pack, int64_t pack_stride, int H, int is_tanh, int lanes_per_member,
+                                  const float* __restrict__ state, const int32_t* __restrict__ action, float* __restrict__ ns_out,
+                                  float* __restrict__ reward, float* __restrict__ done, int n) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    float s[SD], ns[SD], r, d;
+#pragma unroll
+    for (int i = 0; i < SD; ++i) s[i] = state[(int64_t)row * SD + i];
+    se_step_row<SD, AD>(pack + (int64_t)(row / lanes_per_member) * pack_stride, H, is_tanh != 0, s, action[row], lane, ns, r, d);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < SD; ++i) ns_out[(int64_t)row * SD + i] = ns[i];
+        reward[row] = r;
+        done[row] = d;
+    }
+}
+
+template <int SD>
+__global__ void rn_reward_kernel(const float4* __restrict__ pack, int64_t pack_stride, int H, int is_tanh, int rn_type, float gamma,
+                                 int lanes_per_member, const float* __restrict__ s_in, const float* __restrict__ s2_in,
+                                 const float* __restrict__ rr, float* __restrict__ out, int n) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    float s[SD], s2[SD];
+#pragma unroll
+    for (int i = 0; i < SD; ++i) { s[i] = s_in[(int64_t)row * SD + i]; s2[i] = s2_in[(int64_t)row * SD + i]; }
+    float ps = 0.f, ps2 = 0.f;
+    if (rn_type != 0) rn_phi2<SD>(pack + (int64_t)(row / lanes_per_member) * pack_stride, H, is_tanh != 0, s, s2, lane, ps, ps2);
+    if (lane == 0) out[row] = rn_combine(rn_type, gamma, rr[row], ps, ps2);
+}
+
+template <int SD, int AD, int U, int ACT>
+__global__ void qnet_forward_kernel(const float* __restrict__ q_theta, int q_stride, int H, float slope,
+                                    const float* __restrict__ state, float* __restrict__ q_out, int32_t* __restrict__ argmax, int n) {
+    using Core = LaneCore<SD, AD, U, ACT>;
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    Core core;
+    core.load_net(q_theta + (int64_t)row * q_stride, H, lane, core.w1, core.b1, core.w2, core.b2);
+    float s[SD], q[AD];
+#pragma unroll
+    for (int i = 0; i < SD; ++i) s[i] = state[(int64_t)row * SD + i];
+    core.q_forward_row(s, slope, q);
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < AD; ++a) q_out[(int64_t)row * AD + a] = q[a];
+        argmax[row] = Core::argmax_first(q);
+    }
+}
+
+// DDQN.learn on explicit minibatches: rows in the public packed order [s a s' r d] (2*SD+3 floats)
+template <int SD, int AD, int U, int ACT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT, float* m, float* v, int32_t* tcount, int q_stride,
+                 const float* __restrict__ rows, int B, float* __restrict__ loss_out, int n) {
+    using Core = LaneCore<SD, AD, U, ACT>;
+    using RL = RowLayout<SD>;
+    __shared__ __align__(16) float smem_all[kWarpsPerCta][kStageRows * RL::ROWF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int id = blockIdx.x * kWarpsPerCta + warp;
+    if (id >= n) return;
+    float* smem = smem_all[warp];
+    const le_lane_cfg c = *cfg_dev;
+    const int H = c.q_hidden;
+    Core core;
+    const int64_t o = (int64_t)id * q_stride;
+    core.load_net(th + o, H, lane, core.w1, core.b1, core.w2, core.b2);
+    core.load_net(thT + o, H, lane, core.tw1, core.tb1, core.tw2, core.tb2);
+    core.load_net(m + o, H, lane, core.mw1, core.mb1, core.mw2, core.mb2);
+    core.load_net(v + o, H, lane, core.vw1, core.vb1, core.vw2, core.vb2);
+    LearnScalars ls;
+    fill_learn_scalars(ls, c);
+    ls.batch = B;
+    ls.norm = (float)(2.0 / (double)B);
+    const int t0 = tcount[id];
+    ls.b1pow = pow(c.beta1, (double)t0);
+    ls.b2pow = pow(c.beta2, (double)t0);
+    core.zero_grads();
+    float loss_part = 0.f;
+    constexpr int ROWP = 2 * SD + 3;
+    const float* my_rows = rows + (int64_t)id * B * ROWP;
+    for (int sc = 0; sc * kStageRows < B; ++sc) {
+        const int nrows = min(kStageRows, B - sc * kStageRows);
+        const int nfill = (nrows + Core::R - 1) / Core::R * Core::R;
+        for (int rr = lane; rr < nfill; rr += 32) {
+            float* dst = smem + rr * RL::ROWF;
+            const float* src = my_rows + (int64_t)(sc * kStageRows + rr) * ROWP;
+            const bool ok = rr < nrows;
+#pragma unroll
+            for (int i = 0; i < RL::ROWF; ++i) dst[i] = 0.f;
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < SD; ++i) { dst[RL::OFF_S + i] = src[i]; dst[RL::OFF_S2 + i] = src[SD + 1 + i]; }
+                dst[RL::OFF_A] = src[SD]; dst[RL::OFF_R] = src[2 * SD + 1]; dst[RL::OFF_D] = src[2 * SD + 2];
+            }
+        }
+        __syncwarp();
+        loss_part += core.td_rows(smem, nrows, ls, lane);
+        __syncwarp();
+    }
+    const float loss = warp_allreduce_sum(loss_part) / (float)B;
+    core.adam_polyak(ls);
+    core.store_net(th + o, H, lane, core.w1, core.b1, core.w2, core.b2);
+    core.store_net(thT + o, H, lane, core.tw1, core.tb1, core.tw2, core.tb2);
+    core.store_net(m + o, H, lane, core.mw1, core.mb1, core.mw2, core.mb2);
+    core.store_net(v + o, H, lane, core.vw1, core.vb1, core.vw2, core.vb2);
+    if (lane == 0) { loss_out[id] = loss; tcount[id] = t0 + 1; }
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <int SD, int AD, int U, int ACT>
+struct InstanceImpl {
+    static int inner_max_ctas_per_sm() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, inner_loop_kernel<SD, AD, U, ACT>, kWarpsPerCta * 32, 0);
+        return nb;
+    }
+    static cudaError_t launch_inner(const RunParams& P, int grid, cudaStream_t st) {
+        inner_loop_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, 0, st>>>(P);
+        return cudaGetLastError();
+    }
+    static int64_t ring_row_floats() { return RowLayout<SD>::ROWF; }
+    static int64_t se_pack_vec4(int H) { return SePack<SD, AD>::pack_vec4(H); }
+    static int64_t rn_pack_vec4(int H) { return RnPack<SD>::pack_vec4(H); }
+    static cudaError_t launch_pack_se(const float* theta, int P_env, int n_env, int H, const float* slopes, float* out,
+                                      int64_t out_stride_f, cudaStream_t st) {
+        const int64_t total = SePack<SD, AD>::pack_vec4(H) * 4 * n_env;
+        const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        pack_se_kernel<SD, AD><<<grid, 256, 0, st>>>(theta, P_env, n_env, H, slopes[0], slopes[1], slopes[2], out, out_stride_f);
+        return cudaGetLastError();
+    }
+    static cudaError_t launch_pack_rn(const float* theta, int P_env, int n_env, int H, float slope, float* out, int64_t out_stride_f,
+                                      cudaStream_t st) {
+        const int64_t total = RnPack<SD>::pack_vec4(H) * 4 * n_env;
+        const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        pack_rn_kernel<SD><<<grid, 256, 0, st>>>(theta, P_env, n_env, H, slope, out, out_stride_f);
+        return cudaGetLastError();
+    }
+    static cudaError_t launch_se_forward(const float4* pack, int64_t pack_stride, int H, int is_tanh, int lanes_per_member,
+                                         const float* state, const int32_t* action, float* ns, float* reward, float* done, int n,
+                                         cudaStream_t st) {
+        const int grid = (n + 3) / 4;
+        se_forward_kernel<SD, AD><<<grid, 128, 0, st>>>(pack, pack_stride, H, is_tanh, lanes_per_member, state, action, ns, reward, done, n);
+        return cudaGetLastError();
+    }
+    static cudaError_t launch_rn_reward(const float4* pack, int64_t pack_stride, int H, int is_tanh, int rn_type, float gamma,
+                                        int lanes_per_member, const float* s, const float* s2, const float* rr, float* out, int n,
+                                        cudaStream_t st) {
+        const int grid = (n + 3) / 4;
+        rn_reward_kernel<SD><<<grid, 128, 0, st>>>(pack, pack_stride, H, is_tanh, rn_type, gamma, lanes_per_member, s, s2, rr, out, n);
+        return cudaGetLastError();
+    }
+    static cudaError_t launch_qnet_forward(const float* q_theta, int q_stride, int H, float slope, const float* state, float* q_out,
+                                           int32_t* argmax, int n, cudaStream_t st) {
+        const int grid = (n + 3) / 4;
+        qnet_forward_kernel<SD, AD, U, ACT><<<grid, 128, 0, st>>>(q_theta, q_stride, H, slope, state, q_out, argmax, n);
+        return cudaGetLastError();
+    }
+    static cudaError_t launch_td_update(const le_lane_cfg* cfg_dev, float* th, float* thT, float* m, float* v, int32_t* t, int q_stride,
+                                        const float* rows, int B, float* loss, int n, cudaStream_t st) {
+        const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+        td_update_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, 0, st>>>(cfg_dev, th, thT, m, v, t, q_stride, rows, B, loss, n);
+        return cudaGetLastError();
+    }
+    static const InstanceOps* ops() {
+        static const InstanceOps o = {SD, AD, U, ACT, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
+                                      rn_pack_vec4, launch_pack_se, launch_pack_rn, launch_se_forward, launch_rn_reward,
+                                      launch_qnet_forward, launch_td_update};
+        return &o;
+    }
+};
+
+}  // namespace le

@@ -272,7 +272,7 @@ def gen_nes(seed):
         [10, 200, 35.5, 9.4, 150, 200, 60, 12],                 # SURVEY Appendix C (tie between members 1 and 5)
         list(rng.uniform(0, 200, size=8)),
         [50.0] * 8,                                             # all equal
-        [-500, -100, -480, -90, -500, -250, -100, -499],        # Acrobot-like negative scores with ties
+        [-500.0, -100.0, -480.0, -90.0, -500.0, -250.0, -100.0, -499.0],        # Acrobot-like negative scores with ties
     ]
     orig_lists = [[50] * 8, list(rng.uniform(0, 200, size=8)), [50.0] * 8, [-300.0] * 8]
     out = {}

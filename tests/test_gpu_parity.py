@@ -1,0 +1,236 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against (a) golden vectors produced by the UNMODIFIED
+reference (tests/golden, oracle/gen_golden.py) and (b) the CPU restatement (oracle/le_oracle.c) on seeded inputs.
+
+Tolerances (BASELINE.json north_star): SE/RN outputs and TD losses 1e-5 relative in fp32; replay indices,
+Philox words and argmax actions bit-exact away from near-ties.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, nes, philox
+from tests.helpers import cfg_from_bytes, load_golden, rel_err, sync_prefix
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from learning_environments_b200 import ops as _ops
+    assert _ops.version() == 100
+    return _ops
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot"])
+def test_se_forward_vs_reference_golden(ops, tag):
+    g = load_golden("se_step_%s.npz" % tag)
+    cfg = cfg_from_bytes(g["cfg"])
+    ns, r, d = ops.se_forward(cfg, dev(g["theta"])[None], dev(g["states"]), dev(g["actions"], torch.int32))
+    assert rel_err(ns.cpu().numpy(), g["next_states"], 1e-2) < RTOL
+    assert rel_err(r.cpu().numpy(), g["rewards"], 1e-2) < RTOL
+    assert rel_err(d.cpu().numpy(), g["dones"], 1e-2) < RTOL
+
+
+def test_se_forward_population_batched_vs_oracle(ops):
+    """pop members x lanes: row r uses member r // lanes (the batched surface of SURVEY §8b)."""
+    g = load_golden("se_step_cartpole.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    rng = np.random.RandomState(0)
+    pop, lanes = 5, 7
+    thetas = (g["theta"][None] + rng.standard_normal((pop, g["theta"].size)).astype(np.float32) * 0.05).astype(np.float32)
+    states = rng.uniform(-1, 1, size=(pop * lanes, 4)).astype(np.float32)
+    actions = rng.randint(0, 2, size=pop * lanes).astype(np.int32)
+    ns, r, d = ops.se_forward(cfg, dev(thetas), dev(states), dev(actions), lanes_per_member=lanes)
+    ns, r, d = ns.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+    for i in range(pop * lanes):
+        ons, orr, od = c_oracle.se_step(cfg, thetas[i // lanes], states[i], actions[i])
+        assert rel_err(ns[i], ons, 1e-2) < RTOL and rel_err(r[i], orr, 1e-2) < RTOL and rel_err(d[i], od, 1e-2) < RTOL
+
+
+def test_rn_reward_types_vs_reference_golden(ops):
+    g = load_golden("rn_reward_cartpole.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    s, s2 = dev(g["s"], torch.float32), dev(g["s2"], torch.float32)
+    rr = dev(g["real_reward"], torch.float32)
+    for t in (0, 1, 2, 5, 6):
+        cfg.rn_type = t
+        out = ops.rn_reward(cfg, dev(g["theta"])[None], s, s2, rr)
+        assert rel_err(out.cpu().numpy(), g["type%d" % t], 1e-2) < RTOL, t
+    for t in (3, 4, 7, 8, 101, 102):
+        cfg.rn_type = t
+        with pytest.raises(ValueError):
+            ops.rn_reward(cfg, dev(g["theta"])[None], s, s2, rr)
+
+
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn"])
+def test_qnet_forward_argmax_vs_oracle(ops, tag):
+    g = load_golden("td_update_%s.npz" % tag)
+    cfg = cfg_from_bytes(g["cfg"])
+    rng = np.random.RandomState(1)
+    n = 257
+    P = cfg.q_params()
+    thetas = (g["q_init"][None] + rng.standard_normal((n, P)).astype(np.float32) * 0.1).astype(np.float32)
+    states = rng.uniform(-2, 2, size=(n, cfg.sd)).astype(np.float32)
+    q, am = ops.qnet_forward(cfg, dev(thetas), dev(states))
+    q, am = q.cpu().numpy(), am.cpu().numpy()
+    for i in range(n):
+        oq, oa = c_oracle.q_forward(cfg, thetas[i], states[i])
+        assert rel_err(q[i], oq, 1e-2) < RTOL
+        srt = np.sort(oq)
+        if srt[-1] - srt[-2] > 1e-5 * max(1.0, abs(srt[-1])):   # away from near-ties: bit-exact argmax
+            assert am[i] == oa
+
+
+@pytest.mark.parametrize("tag,kind", [("cartpole", 0), ("acrobot", 1)])
+def test_real_env_step_vs_golden(ops, tag, kind):
+    g = load_golden("real_env_%s.npz" % tag)
+    sd = 4 if kind == 0 else 6
+    max_steps = 200 if kind == 0 else 500
+    for ep in range(int(g["n_episodes"])):
+        states = g["ep%d_states" % ep]
+        st = dev(states[:1].copy())
+        el = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for t, a in enumerate(g["ep%d_actions" % ep]):
+            obs, r, d = ops.real_env_step(kind, max_steps, st, el, dev(np.array([a], np.int32)), sd)
+            got = st.cpu().numpy()[0]
+            # fp64 dynamics: identical op order, only sin/cos implementations differ (<= 2 ulp each)
+            assert np.allclose(got, states[t + 1], rtol=1e-12, atol=1e-13), (tag, ep, t)
+            assert np.allclose(obs.cpu().numpy()[0], g["ep%d_obs" % ep][t + 1].astype(np.float32), rtol=2e-7, atol=1e-7)
+            assert float(r) == np.float32(g["ep%d_rewards" % ep][t]) and bool(d.item()) == bool(g["ep%d_dones" % ep][t])
+        assert int(el.item()) == len(g["ep%d_actions" % ep])
+
+
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn"])
+def test_td_update_vs_reference_golden(ops, tag):
+    g = load_golden("td_update_%s.npz" % tag)
+    cfg = cfg_from_bytes(g["cfg"])
+    n = 3  # three identical lanes: also checks lane indexing
+    th = dev(np.repeat(g["q_init"][None], n, 0))
+    thT = th.clone()
+    m = torch.zeros_like(th)
+    v = torch.zeros_like(th)
+    t = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for k in range(g["rows"].shape[0]):
+        rows = dev(np.repeat(g["rows"][k][None], n, 0))
+        loss = ops.td_update(cfg, th, thT, m, v, t, rows).cpu().numpy()
+        assert rel_err(loss, np.repeat(g["losses"][k], n)) < RTOL, (k, loss, g["losses"][k])
+        scale = np.maximum(np.abs(g["thetas"][k]), 1e-2)
+        for lane in range(n):
+            assert np.max(np.abs(th[lane].cpu().numpy() - g["thetas"][k]) / scale) < 5e-5
+            assert np.max(np.abs(thT[lane].cpu().numpy() - g["targets"][k]) / scale) < 5e-5
+    assert t.cpu().tolist() == [g["rows"].shape[0]] * n
+    assert np.max(np.abs(m[0].cpu().numpy() - g["adam_m"])) < 1e-5 * max(1.0, np.abs(g["adam_m"]).max())
+    assert np.max(np.abs(v[0].cpu().numpy() - g["adam_v"])) < 1e-5 * max(1.0, np.abs(g["adam_v"]).max())
+
+
+def _run_fused(ops, cfg, env_theta, keys, q_init, trace_cap=0, n_env=1, env_index=None):
+    n = len(keys)
+    bufs = ops.InnerLoopBuffers(cfg, n, n_env, "cuda", trace_cap=trace_cap, want_q_final=True)
+    th = None if env_theta is None else dev(np.asarray(env_theta, np.float32).reshape(n_env, -1))
+    ei = None if env_index is None else dev(np.asarray(env_index, np.int32))
+    ops.inner_loop_run(bufs, cfg, th, ei, ops.keys_tensor(keys, "cuda"), q_init=None if q_init is None else dev(q_init))
+    torch.cuda.synchronize()
+    return bufs
+
+
+@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest"])
+def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
+    """The fused persistent kernel, one lane, against the reference's own BaseAgent.train trace."""
+    g = load_golden("trajectory_%s.npz" % tag)
+    cfg = cfg_from_bytes(g["cfg"])
+    key = [tuple(int(k) for k in g["key"])]
+    cap = len(g["action"])
+    bufs = _run_fused(ops, cfg, g["env_theta"], key, g["q_init"][None], trace_cap=cap)
+    tr = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in bufs.trace.items()}
+    res = bufs.results()[0]
+    n_sync = sync_prefix(g["action"], tr["action"])
+    assert n_sync >= min(cap, 150), "kernel left the reference trajectory after %d steps" % n_sync
+    n = n_sync
+    assert np.array_equal(tr["explore"][:n], g["explore"][:n])
+    assert rel_err(tr["next_state"][:n], g["next_state"][:n], 1e-2) < 2e-4
+    assert rel_err(tr["reward"][:n], g["reward"][:n], 1e-2) < 2e-4
+    assert np.array_equal(np.isnan(tr["loss"][:n]), np.isnan(g["loss"][:n]))
+    k = np.nonzero(~np.isnan(g["loss"][:n]))[0]
+    assert rel_err(tr["loss"][k[:20]], g["loss"][k[:20]]) < RTOL      # TD losses: 1e-5 before drift is amplified
+    assert rel_err(tr["loss"][k], g["loss"][k]) < 5e-3
+    if n_sync == int(g["train_steps"]) == int(res["train_steps"]):
+        assert int(res["n_episodes"]) == len(g["rewards"])
+        assert np.array_equal(bufs.lengths.cpu().numpy()[0, :len(g["lengths"])], g["lengths"])
+        assert np.allclose(bufs.rewards.cpu().numpy()[0, :len(g["rewards"])], g["rewards"], rtol=1e-4, atol=1e-4)
+        assert np.allclose(bufs.test_rewards.cpu().numpy()[0], g["test_rewards"])
+
+
+def test_fused_many_lanes_vs_oracle(ops):
+    """64 lanes (8 SE members x 8 keys) through the lane queue; every lane vs the CPU restatement."""
+    g = load_golden("trajectory_cartpole_se.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 3, 2, 1
+    rng = np.random.RandomState(3)
+    n_env, per = 8, 8
+    thetas = (g["env_theta"][None] + rng.standard_normal((n_env, g["env_theta"].size)).astype(np.float32) * 0.02).astype(np.float32)
+    keys = [philox.lane_key(7, 0, i // per, 0, i % per) for i in range(n_env * per)]
+    env_index = np.arange(n_env * per, dtype=np.int32) // per
+    bufs = _run_fused(ops, cfg, thetas, keys, None, n_env=n_env, env_index=env_index)
+    res = bufs.results()
+    oracle = c_oracle.run_lanes(cfg, thetas, env_index, np.array(keys, np.uint32), n_threads=8)
+    # integer bookkeeping is exact while trajectories agree; chaos (fp32 summation order) may move a few lanes
+    same_steps = (res["train_steps"] == oracle["train_steps"])
+    assert same_steps.mean() >= 0.8, same_steps
+    ok = same_steps & (res["n_episodes"] == oracle["n_episodes"])
+    assert np.array_equal(res["learn_iters"][ok], oracle["learn_iters"][ok])
+    assert np.allclose(res["score"][ok], oracle["score"][ok], atol=1e-9) or (np.isclose(res["score"][ok], oracle["score"][ok]).mean() > 0.8)
+    # Philox-initialised Q-nets: first-episode (pre-learning) lengths depend only on init + SE + RNG -> exact
+    assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0])
+
+
+def test_host_buffer_entry_matches_device_entry(ops):
+    g = load_golden("trajectory_cartpole_se.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    cfg.train_episodes, cfg.test_episodes = 3, 2
+    keys = [(11, 12), (13, 14), (15, 16), (17, 18), (19, 20)]
+    bufs = _run_fused(ops, cfg, g["env_theta"], keys, None)
+    dres = bufs.results()
+    h = ops.inner_loop_run_host(cfg, g["env_theta"], None, keys, want_q_final=True)
+    for f in ("n_episodes", "train_steps", "learn_iters", "test_steps", "score"):
+        assert np.array_equal(h["out"][f], dres[f]), f
+    assert np.array_equal(h["rewards"], bufs.rewards.cpu().numpy())
+    assert np.array_equal(h["q_final"], bufs.q_final.cpu().numpy())     # same kernel, same order: bit-exact
+
+
+def test_nes_noise_perturb_update(ops):
+    P, pop, seed, gen, std = 2247, 16, 1234, 5, 0.0124
+    eps = ops.nes_noise(P, 0, pop, seed, gen, std, "cuda").cpu().numpy()
+    want = np.stack([nes.noise(seed, gen, i, P, std) for i in range(pop)])
+    # Philox words are exact; Box-Muller runs in fp64 on both sides, libm log/sincos differ by <= 2 ulp(fp64):
+    # after rounding to fp32 the normals agree to 1 ulp (almost always exactly)
+    assert np.max(np.abs(eps - want) / np.maximum(np.abs(want), 1e-6)) < 2.5e-7
+    assert (eps == want).mean() > 0.999
+    sub = ops.nes_noise(P, 5, 3, seed, gen, std, "cuda").cpu().numpy()
+    assert np.array_equal(sub, eps[5:8])                                  # member offset = sharding over ranks
+    rng = np.random.RandomState(0)
+    theta = rng.standard_normal(P).astype(np.float32) * 0.1
+    pert = ops.nes_perturb(dev(theta), pop, 4, 6, seed, gen, std).cpu().numpy().reshape(6, 3, P)
+    assert np.array_equal(pert[:, 0], np.repeat(theta[None], 6, 0))
+    assert np.array_equal(pert[:, 1], theta[None] + eps[4:10]) and np.array_equal(pert[:, 2], theta[None] - eps[4:10])
+    # update_env: device update with regenerated noise == numpy restatement fed the device's eps, bit-exact
+    scores = rng.uniform(0, 200, size=pop)
+    w = nes.score_transform(scores, scores * 0.5, 3)
+    sign = np.where(rng.uniform(size=pop) < 0.5, -1.0, 1.0).astype(np.float32)
+    for wd in (0.0, 0.01):
+        coef = np.array([np.float32(0.148 * wi) for wi in w], np.float32)
+        th = dev(theta.copy())
+        ops.nes_update(th, pop, seed, gen, std, wd, dev(coef), dev(sign))
+        want_th = nes.update_env(theta, eps * sign[:, None], w, 0.148, weight_decay=wd)
+        assert np.array_equal(th.cpu().numpy(), want_th)
+    # sharded partial sums (allreduce path) add up to the same update within fp32 reassociation
+    parts = [ops.nes_partial_update(P, lo, lo + 4, seed, gen, std, dev(coef), dev(sign)).cpu().numpy() for lo in range(0, pop, 4)]
+    full = nes.update_env(theta, eps * sign[:, None], w, 0.148) - theta
+    assert np.allclose(sum(parts), full, rtol=1e-4, atol=1e-7)
