@@ -120,11 +120,11 @@ __global__ void nes_perturb_kernel(const float* __restrict__ theta, int P, int m
             const int p = blk * 4 + k;
             if (p < P) {
                 const float th = theta[p];
-                const float e = z[k] * noise_std;  // torch.normal(0,1) * noise_std
+                const float e = __fmul_rn(z[k], noise_std);  // torch.normal(0,1) * noise_std (a rounded fp32 tensor)
                 float* o = out + (int64_t)mloc * 3 * P + p;
                 o[0] = th;
-                o[P] = th + e;        // l_orig.weight + l_eps.weight
-                o[2 * (int64_t)P] = th - e;  // l_orig.weight - l_eps.weight
+                o[P] = __fadd_rn(th, e);               // l_orig.weight + l_eps.weight   (no FMA contraction)
+                o[2 * (int64_t)P] = __fsub_rn(th, e);  // l_orig.weight - l_eps.weight
             }
         }
     }
@@ -140,7 +140,7 @@ __global__ void nes_noise_kernel(int P, int member_offset, int n_members, uint32
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int p = blk * 4 + k;
-            if (p < P) eps[(int64_t)mloc * P + p] = z[k] * noise_std;
+            if (p < P) eps[(int64_t)mloc * P + p] = __fmul_rn(z[k], noise_std);
         }
     }
 }

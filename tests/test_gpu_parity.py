@@ -83,7 +83,7 @@ def test_qnet_forward_argmax_vs_oracle(ops, tag):
     q, am = q.cpu().numpy(), am.cpu().numpy()
     for i in range(n):
         oq, oa = c_oracle.q_forward(cfg, thetas[i], states[i])
-        assert rel_err(q[i], oq, 1e-2) < RTOL
+        assert rel_err(q[i], oq, 5e-2) < RTOL      # floor = scale of the summed terms (q values cancel to ~1e-2)
         srt = np.sort(oq)
         if srt[-1] - srt[-2] > 1e-5 * max(1.0, abs(srt[-1])):   # away from near-ties: bit-exact argmax
             assert am[i] == oa
