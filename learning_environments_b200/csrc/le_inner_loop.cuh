@@ -26,12 +26,19 @@ struct RunParams {
 
 constexpr int kWarpsPerCta = 4;
 
+
+// Per-warp shared memory: [stage rows | test-phase weight image (aliased)] [Adam m, v] [lane configuration]
 template <int SD, int AD, int U>
 struct SmemWarp {
+    using SL = StageLayout<SD>;
     static constexpr int PUP = ((SD + 1 + AD) + 3) / 4 * 4;  // padded per-unit record of the test-phase weight image
-    static constexpr int STAGE_F = kStageRows * RowLayout<SD>::ROWF;
+    static constexpr int STAGE_F = SL::ROWS * SL::STAGE_F;
     static constexpr int QW_F = U * 32 * PUP;
-    static constexpr int FLOATS = STAGE_F > QW_F ? STAGE_F : QW_F;
+    static constexpr int BUF_F = STAGE_F > QW_F ? STAGE_F : QW_F;
+    static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
+    static constexpr int CFG_F = (sizeof(le_lane_cfg) + 15) / 16 * 4;
+    static constexpr int FLOATS = BUF_F + MV_F + CFG_F;
+    static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F;
 };
 
 __device__ __forceinline__ float4 ld_cg_f4(const float4* p) { return __ldcg(p); }
@@ -43,6 +50,20 @@ __device__ __forceinline__ double mean_window(const double* vals, int len, int n
     double s = 0.0;
     for (int i = lo; i < hi; ++i) s += vals[i];
     return s / ((double)(hi - lo) + 1e-9);
+}
+
+// One replay row (HBM layout RowLayout) -> stage layout: inputs duplicated for FFMA2, action as int bits.
+template <int SD>
+__device__ __forceinline__ void stage_row(float* dst, const float (&rowv)[RowLayout<SD>::ROWF]) {
+    using RL = RowLayout<SD>;
+    using SL = StageLayout<SD>;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < SD; i += 2) {
+        d4[(SL::OFF_S + 2 * i) / 4] = make_float4(rowv[RL::OFF_S + i], rowv[RL::OFF_S + i], rowv[RL::OFF_S + i + 1], rowv[RL::OFF_S + i + 1]);
+        d4[(SL::OFF_S2 + 2 * i) / 4] = make_float4(rowv[RL::OFF_S2 + i], rowv[RL::OFF_S2 + i], rowv[RL::OFF_S2 + i + 1], rowv[RL::OFF_S2 + i + 1]);
+    }
+    d4[SL::OFF_A / 4] = make_float4(__int_as_float((int)rowv[RL::OFF_A]), rowv[RL::OFF_R], rowv[RL::OFF_D], 0.f);
 }
 
 template <int SD, int AD, int U, int ACT>
@@ -61,10 +82,10 @@ struct FusedLane {
         for (int u = 0; u < U; ++u) {
             float* rec = smem + (lane + 32 * u) * PUP;
 #pragma unroll
-            for (int i = 0; i < SD; ++i) rec[i] = core.w1[u][i];
-            rec[SD] = core.b1[u];
+            for (int i = 0; i < SD; ++i) rec[i] = core.wt1[u][i].x;
+            rec[SD] = core.bt1[u].x;
 #pragma unroll
-            for (int a = 0; a < AD; ++a) rec[SD + 1 + a] = core.w2[u][a];
+            for (int a = 0; a < AD; ++a) rec[SD + 1 + a] = core.wt2[u][a].x;
         }
         __syncwarp();
         const int H = c.q_hidden;
@@ -91,7 +112,7 @@ struct FusedLane {
                         float z = rec[SD];
 #pragma unroll
                         for (int i = 0; i < SD; ++i) z = fmaf(rec[i], obs[i], z);
-                        const float h = q_act<ACT>(z, slope);
+                        const float h = act_one<ACT>(z, slope);
 #pragma unroll
                         for (int a = 0; a < AD; ++a) q[a] = fmaf(h, rec[SD + 1 + a], q[a]);
                     }
@@ -120,7 +141,15 @@ struct FusedLane {
     }
 
     static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane) {
-        const le_lane_cfg c = P.cfg[P.n_cfg == 1 ? 0 : lane_id];
+        using SL = StageLayout<SD>;
+        float* mv = smem + SW::OFF_MV;
+        {   // lane configuration -> shared memory (read on demand instead of pinning ~46 registers)
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(P.cfg + (P.n_cfg == 1 ? 0 : lane_id));
+            uint32_t* dst = reinterpret_cast<uint32_t*>(smem + SW::OFF_CFG);
+            for (int i = lane; i < (int)(sizeof(le_lane_cfg) / 4); i += 32) dst[i] = src[i];
+            __syncwarp();
+        }
+        const le_lane_cfg& c = *reinterpret_cast<const le_lane_cfg*>(smem + SW::OFF_CFG);
         const uint32_t k0 = P.keys[2 * lane_id], k1 = P.keys[2 * lane_id + 1];
         const float4* pack = P.env_pack + (int64_t)(P.env_index ? P.env_index[lane_id] : 0) * P.env_pack_stride;
         const bool env_tanh = c.env_act == LE_ACT_TANH;
@@ -133,10 +162,10 @@ struct FusedLane {
         const bool tracing = P.trace.cap > 0 && lane_id == P.trace_lane;
 
         Core core;
-        if (P.q_init) core.load_net(P.q_init + (int64_t)lane_id * P.q_stride, H, lane, core.w1, core.b1, core.w2, core.b2);
+        if (P.q_init) core.load_net(P.q_init + (int64_t)lane_id * P.q_stride, H, lane, 0);
         else core.init_online(H, lane, k0, k1);
         core.copy_online_to_target();  // model_target.load_state_dict(model.state_dict())   agents/DDQN.py:36
-        core.zero_moments();
+        Core::zero_moments(mv, lane);
         LearnScalars ls;
         fill_learn_scalars(ls, c);
 
@@ -206,11 +235,12 @@ struct FusedLane {
                     core.zero_grads();
                     float loss_part = 0.f;
                     const int B = ls.batch;
-                    for (int sc = 0; sc * kStageRows < B; ++sc) {
-                        const int nrows = min(kStageRows, B - sc * kStageRows);
+                    for (int sc = 0; sc * SL::ROWS < B; ++sc) {
+                        const int nrows = min(SL::ROWS, B - sc * SL::ROWS);
                         const int nfill = (nrows + Core::R - 1) / Core::R * Core::R;
-                        // replay_buffer.sample: idx = randint(0, size, B) on the P_SAMPLE stream (utils.py:35)
-                        const int blk = sc * 32 + lane;
+                        // replay_buffer.sample: idx = randint(0, size, B) on the P_SAMPLE stream (utils.py:35);
+                        // thread t gathers the 4 rows of Philox block (sc*ROWS/4 + t) and stages them input-duplicated
+                        const int blk = sc * (SL::ROWS / 4) + lane;
                         if (4 * lane < nfill) {
                             const u32x4 w = philox4x32_10((uint32_t)learn_iters, (uint32_t)blk, LE_P_SAMPLE, 0u, k0, k1);
                             float4 v[4][RL::ROW_VEC];
@@ -224,9 +254,10 @@ struct FusedLane {
                             }
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                float4* dsts = reinterpret_cast<float4*>(smem + (4 * lane + kk) * RL::ROWF);
+                                float rowv[RL::ROWF];
 #pragma unroll
-                                for (int q = 0; q < RL::ROW_VEC; ++q) dsts[q] = v[kk][q];
+                                for (int q = 0; q < RL::ROW_VEC; ++q) { rowv[4 * q] = v[kk][q].x; rowv[4 * q + 1] = v[kk][q].y; rowv[4 * q + 2] = v[kk][q].z; rowv[4 * q + 3] = v[kk][q].w; }
+                                stage_row<SD>(smem + (4 * lane + kk) * SL::STAGE_F, rowv);
                             }
                         }
                         __syncwarp();
@@ -234,7 +265,7 @@ struct FusedLane {
                         __syncwarp();
                     }
                     loss = warp_allreduce_sum(loss_part) / (float)B;
-                    core.adam_polyak(ls);
+                    core.adam_polyak(ls, mv, lane);
                     learn_iters += 1;
                 }
                 if (tracing && train_steps < P.trace.cap && lane == 0) {
@@ -267,7 +298,7 @@ struct FusedLane {
         }
         double score = 0.0;
         if (c.final_test) score = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, test_rewards, test_steps);
-        if (P.q_final) core.store_net(P.q_final + (int64_t)lane_id * P.q_stride, H, lane, core.w1, core.b1, core.w2, core.b2);
+        if (P.q_final) core.store_net(P.q_final + (int64_t)lane_id * P.q_stride, H, lane, 0);
         if (lane == 0) {
             le_lane_out o;
             o.n_episodes = n_ep; o.timed_out = timed_out; o.train_steps = train_steps; o.learn_iters = learn_iters;
@@ -278,12 +309,12 @@ struct FusedLane {
 };
 
 template <int SD, int AD, int U, int ACT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) inner_loop_kernel(const RunParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (U <= 2 ? 3 : 1)) inner_loop_kernel(const RunParams P) {
     using SW = SmemWarp<SD, AD, U>;
-    __shared__ __align__(16) float smem_all[kWarpsPerCta][SW::FLOATS];
+    extern __shared__ __align__(16) float smem_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * kWarpsPerCta + warp;
-    float* smem = smem_all[warp];
+    float* smem = smem_dyn + warp * SW::FLOATS;
     for (;;) {
         int lane_id = 0;
         if (lane == 0) lane_id = atomicAdd(P.work_counter, 1);

@@ -80,7 +80,7 @@ __global__ void qnet_forward_kernel(const float* __restrict__ q_theta, int q_str
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
     Core core;
-    core.load_net(q_theta + (int64_t)row * q_stride, H, lane, core.w1, core.b1, core.w2, core.b2);
+    core.load_net(q_theta + (int64_t)row * q_stride, H, lane, 0);
     float s[SD], q[AD];
 #pragma unroll
     for (int i = 0; i < SD; ++i) s[i] = state[(int64_t)row * SD + i];
@@ -99,19 +99,21 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
                  const float* __restrict__ rows, int B, float* __restrict__ loss_out, int n) {
     using Core = LaneCore<SD, AD, U, ACT>;
     using RL = RowLayout<SD>;
-    __shared__ __align__(16) float smem_all[kWarpsPerCta][kStageRows * RL::ROWF];
+    using SL = StageLayout<SD>;
+    using SW = SmemWarp<SD, AD, U>;
+    extern __shared__ __align__(16) float smem_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int id = blockIdx.x * kWarpsPerCta + warp;
     if (id >= n) return;
-    float* smem = smem_all[warp];
+    float* smem = smem_dyn + warp * SW::FLOATS;
+    float* mv = smem + SW::OFF_MV;
     const le_lane_cfg c = *cfg_dev;
     const int H = c.q_hidden;
     Core core;
     const int64_t o = (int64_t)id * q_stride;
-    core.load_net(th + o, H, lane, core.w1, core.b1, core.w2, core.b2);
-    core.load_net(thT + o, H, lane, core.tw1, core.tb1, core.tw2, core.tb2);
-    core.load_net(m + o, H, lane, core.mw1, core.mb1, core.mw2, core.mb2);
-    core.load_net(v + o, H, lane, core.vw1, core.vb1, core.vw2, core.vb2);
+    core.load_net(th + o, H, lane, 0);
+    core.load_net(thT + o, H, lane, 1);
+    Core::load_moments(mv, m + o, v + o, H, lane);
     LearnScalars ls;
     fill_learn_scalars(ls, c);
     ls.batch = B;
@@ -123,44 +125,48 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
     float loss_part = 0.f;
     constexpr int ROWP = 2 * SD + 3;
     const float* my_rows = rows + (int64_t)id * B * ROWP;
-    for (int sc = 0; sc * kStageRows < B; ++sc) {
-        const int nrows = min(kStageRows, B - sc * kStageRows);
+    for (int sc = 0; sc * SL::ROWS < B; ++sc) {
+        const int nrows = min(SL::ROWS, B - sc * SL::ROWS);
         const int nfill = (nrows + Core::R - 1) / Core::R * Core::R;
         for (int rr = lane; rr < nfill; rr += 32) {
-            float* dst = smem + rr * RL::ROWF;
-            const float* src = my_rows + (int64_t)(sc * kStageRows + rr) * ROWP;
-            const bool ok = rr < nrows;
+            const float* src = my_rows + (int64_t)(sc * SL::ROWS + rr) * ROWP;
+            float rowv[RL::ROWF];
 #pragma unroll
-            for (int i = 0; i < RL::ROWF; ++i) dst[i] = 0.f;
-            if (ok) {
+            for (int i = 0; i < RL::ROWF; ++i) rowv[i] = 0.f;
+            if (rr < nrows) {
 #pragma unroll
-                for (int i = 0; i < SD; ++i) { dst[RL::OFF_S + i] = src[i]; dst[RL::OFF_S2 + i] = src[SD + 1 + i]; }
-                dst[RL::OFF_A] = src[SD]; dst[RL::OFF_R] = src[2 * SD + 1]; dst[RL::OFF_D] = src[2 * SD + 2];
+                for (int i = 0; i < SD; ++i) { rowv[RL::OFF_S + i] = src[i]; rowv[RL::OFF_S2 + i] = src[SD + 1 + i]; }
+                rowv[RL::OFF_A] = src[SD]; rowv[RL::OFF_R] = src[2 * SD + 1]; rowv[RL::OFF_D] = src[2 * SD + 2];
             }
+            stage_row<SD>(smem + rr * SL::STAGE_F, rowv);
         }
         __syncwarp();
         loss_part += core.td_rows(smem, nrows, ls, lane);
         __syncwarp();
     }
     const float loss = warp_allreduce_sum(loss_part) / (float)B;
-    core.adam_polyak(ls);
-    core.store_net(th + o, H, lane, core.w1, core.b1, core.w2, core.b2);
-    core.store_net(thT + o, H, lane, core.tw1, core.tb1, core.tw2, core.tb2);
-    core.store_net(m + o, H, lane, core.mw1, core.mb1, core.mw2, core.mb2);
-    core.store_net(v + o, H, lane, core.vw1, core.vb1, core.vw2, core.vb2);
+    core.adam_polyak(ls, mv, lane);
+    core.store_net(th + o, H, lane, 0);
+    core.store_net(thT + o, H, lane, 1);
+    __syncwarp();
+    Core::store_moments(mv, m + o, v + o, H, lane);
     if (lane == 0) { loss_out[id] = loss; tcount[id] = t0 + 1; }
 }
 
 // ------------------------------------------------------------------------------------------------------
 template <int SD, int AD, int U, int ACT>
 struct InstanceImpl {
+    static constexpr size_t kSmemBytes = (size_t)kWarpsPerCta * SmemWarp<SD, AD, U>::FLOATS * sizeof(float);
     static int inner_max_ctas_per_sm() {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, inner_loop_kernel<SD, AD, U, ACT>, kWarpsPerCta * 32, 0);
+        cudaFuncSetAttribute(inner_loop_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, inner_loop_kernel<SD, AD, U, ACT>, kWarpsPerCta * 32, kSmemBytes);
         return nb;
     }
     static cudaError_t launch_inner(const RunParams& P, int grid, cudaStream_t st) {
-        inner_loop_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, 0, st>>>(P);
+        cudaError_t e = cudaFuncSetAttribute(inner_loop_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+        inner_loop_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, kSmemBytes, st>>>(P);
         return cudaGetLastError();
     }
     static int64_t ring_row_floats() { return RowLayout<SD>::ROWF; }
@@ -203,7 +209,9 @@ struct InstanceImpl {
     static cudaError_t launch_td_update(const le_lane_cfg* cfg_dev, float* th, float* thT, float* m, float* v, int32_t* t, int q_stride,
                                         const float* rows, int B, float* loss, int n, cudaStream_t st) {
         const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-        td_update_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, 0, st>>>(cfg_dev, th, thT, m, v, t, q_stride, rows, B, loss, n);
+        cudaError_t e = cudaFuncSetAttribute(td_update_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+        td_update_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, kSmemBytes, st>>>(cfg_dev, th, thT, m, v, t, q_stride, rows, B, loss, n);
         return cudaGetLastError();
     }
     static const InstanceOps* ops() {
