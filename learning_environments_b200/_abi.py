@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "lible_b200.so")
+LIB_PATH = os.path.join(_HERE, "csrc", os.environ.get("LE_LIB_NAME", "lible_b200.so"))
 
 ACT_IDS = {"tanh": 0, "relu": 1, "leakyrelu": 2, "prelu": 3, "identity": 4}
 ENV_SE, ENV_RN, ENV_REAL = 0, 1, 2

@@ -13,9 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["le_api.cu", "le_inst_cp_tanh.cu", "le_inst_cp_leaky.cu", "le_inst_ac_tanh.cu", "le_inst_ac_leaky.cu"]
 HEADERS = ["le_common.cuh", "le_lane.cuh", "le_envpack.cuh", "le_inner_loop.cuh", "le_instance.cuh",
            os.path.join("..", "..", "include", "le_b200.h")]
-OUT = os.path.join(HERE, "lible_b200.so")
+OUT = os.path.join(HERE, os.environ.get("LE_LIB_NAME", "lible_b200.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+EXTRA = os.environ.get("LE_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
 

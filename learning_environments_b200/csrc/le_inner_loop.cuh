@@ -27,7 +27,7 @@ struct RunParams {
 constexpr int kWarpsPerCta = 4;
 
 
-// Per-warp shared memory: [stage rows | test-phase weight image (aliased)] [Adam m, v] [lane configuration]
+// Per-warp shared memory: [stage rows | test-phase weight image (aliased)] [Adam m, v] [lane configuration] [reduction]
 template <int SD, int AD, int U>
 struct SmemWarp {
     using SL = StageLayout<SD>;
@@ -37,8 +37,9 @@ struct SmemWarp {
     static constexpr int BUF_F = STAGE_F > QW_F ? STAGE_F : QW_F;
     static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
     static constexpr int CFG_F = (sizeof(le_lane_cfg) + 15) / 16 * 4;
-    static constexpr int FLOATS = BUF_F + MV_F + CFG_F;
-    static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F;
+    static constexpr int RED_F = 8 * (1 + AD) * 32 * 2;  // LaneCore::RED_F: cross-lane reduction buffer
+    static constexpr int FLOATS = BUF_F + MV_F + CFG_F + RED_F;
+    static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F, OFF_RED = BUF_F + MV_F + CFG_F;
 };
 
 __device__ __forceinline__ float4 ld_cg_f4(const float4* p) { return __ldcg(p); }
@@ -261,7 +262,7 @@ struct FusedLane {
                             }
                         }
                         __syncwarp();
-                        loss_part += core.td_rows(smem, nrows, ls, lane);
+                        loss_part += core.td_rows(smem, smem + SW::OFF_RED, nrows, ls, lane);
                         __syncwarp();
                     }
                     loss = warp_allreduce_sum(loss_part) / (float)B;
@@ -308,8 +309,11 @@ struct FusedLane {
     }
 };
 
+#ifndef LE_MIN_CTAS_U2
+#define LE_MIN_CTAS_U2 3
+#endif
 template <int SD, int AD, int U, int ACT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (U <= 2 ? 3 : 1)) inner_loop_kernel(const RunParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (U <= 2 ? LE_MIN_CTAS_U2 : 1)) inner_loop_kernel(const RunParams P) {
     using SW = SmemWarp<SD, AD, U>;
     extern __shared__ __align__(16) float smem_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -141,7 +141,7 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
             stage_row<SD>(smem + rr * SL::STAGE_F, rowv);
         }
         __syncwarp();
-        loss_part += core.td_rows(smem, nrows, ls, lane);
+        loss_part += core.td_rows(smem, smem + SW::OFF_RED, nrows, ls, lane);
         __syncwarp();
     }
     const float loss = warp_allreduce_sum(loss_part) / (float)B;
