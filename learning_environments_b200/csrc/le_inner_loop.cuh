@@ -24,7 +24,10 @@ struct RunParams {
     le_trace trace; int trace_lane;
 };
 
-constexpr int kWarpsPerCta = 4;
+#ifndef LE_WARPS_PER_CTA
+#define LE_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = LE_WARPS_PER_CTA;
 
 
 // Per-warp shared memory: [stage rows | test-phase weight image (aliased)] [Adam m, v] [lane configuration] [reduction]
@@ -310,7 +313,7 @@ struct FusedLane {
 };
 
 #ifndef LE_MIN_CTAS_U2
-#define LE_MIN_CTAS_U2 3
+#define LE_MIN_CTAS_U2 2
 #endif
 template <int SD, int AD, int U, int ACT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (U <= 2 ? LE_MIN_CTAS_U2 : 1)) inner_loop_kernel(const RunParams P) {
