@@ -161,7 +161,8 @@ int64_t le_inner_loop_workspace_bytes(const le_lane_cfg* cfg, int n_lanes, int n
 
 /* The launch plan behind the two calls above/below (diagnostics for bench.py / DESIGN.md): CTAs, resident
  * warp slots, replay ring capacity in rows, hidden units per thread of the selected kernel set. */
-int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid, int* slots, int* ring_cap, int* units);
+int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid, int* slots, int* ring_cap, int* units,
+                       int64_t* ring_offset_bytes /* offset of warp slot 0's replay ring inside the workspace */);
 
 /*
  * Runs n_lanes complete `calc_score`s (agents/GTN_worker.py:187-221) — train() with ε-greedy acting
@@ -181,14 +182,15 @@ int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid
  *   rewards_dev    [n_lanes][train_episodes] doubles: avg_meter_reward raw data (base_agent.py:153)
  *   lengths_dev    [n_lanes][train_episodes] int32: episode lengths
  *   test_rewards_dev [n_lanes][test_episodes] doubles: final test() rewards
+ *   test_lengths_dev NULL or [n_lanes][test_episodes] int32: final test() episode lengths
  *   workspace_dev  le_inner_loop_workspace_bytes() bytes
  *   trace_dev      NULL or one le_trace (device pointers inside) that records lane `trace_lane`
  */
 int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* cfg_host0,
                       const float* env_theta_dev, int n_env, const int32_t* env_index_dev, const uint32_t* keys_dev,
                       const float* q_init_dev, float* q_final_dev, int n_lanes, le_lane_out* out_dev,
-                      double* rewards_dev, int32_t* lengths_dev, double* test_rewards_dev, void* workspace_dev,
-                      int64_t workspace_bytes, const le_trace* trace_host, int trace_lane, void* stream);
+                      double* rewards_dev, int32_t* lengths_dev, double* test_rewards_dev, int32_t* test_lengths_dev,
+                      void* workspace_dev, int64_t workspace_bytes, const le_trace* trace_host, int trace_lane, void* stream);
 
 /* Host-buffer convenience wrapper of le_inner_loop_run (the reference-facing call a GTN worker would
  * make: everything in host memory, H2D/D2H inside).  Arrays as above but HOST pointers.              */

@@ -1,0 +1,327 @@
+"""Agent side of the drop-in API: DDQN / DDQN_vary and select_agent with the reference's surface
+
+    agents/base_agent.py:64-227  train(env, test_env=None, time_remaining=1e9) / test(env, time_remaining=1e9)
+                                 -> (reward_list, episode_length_list, replay_buffer)
+    agents/DDQN.py:14-120        learn / select_train_action / select_test_action / update_parameters_per_episode /
+                                 reset_optimizer, attributes model, model_target, eps, it, full_config
+    agents/DDQN_vary.py:26-59    sampled lr / batch_size / hidden_size / hidden_layer
+    agents/agent_utils.py:15-66  select_agent(config, agent_name)
+
+train()/test() hand the WHOLE loop (acting, env step, replay append, TD update, per-episode test, early-out) to the
+fused persistent kernel as one lane; learn()/select_*_action() are the step-by-step forms on the unit kernels.
+The Q-net parameters, the target net and Adam's moments are flat CUDA tensors in torch's layout; `model` /
+`model_target` are nn.Modules whose parameters VIEW those tensors, so state_dict() matches the reference's keys.
+"""
+import copy
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import config as le_config
+from . import ops
+from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, REAL_ENV_IDS, LaneCfg
+from .envs import EnvFactory, EnvWrapper, _cuda_device, build_nn_from_config
+from .rng import lane_keys
+from .utils import ReplayBuffer, to_one_hot_encoding
+
+#: training env steps per second assumed when a wall-clock `time_remaining` is mapped onto the deterministic
+#: step budget of the kernel (the reference's time budget is wall-clock on one CPU core: ~800 steps/s).
+STEPS_PER_SECOND = 800.0
+
+
+class Critic_DQN(nn.Module):
+    """models/actor_critic.py:84-91 with parameters that are views into one flat tensor."""
+
+    def __init__(self, state_dim, action_dim, agent_name, config, flat=None):
+        super().__init__()
+        self.net = build_nn_from_config(input_dim=state_dim, output_dim=action_dim, nn_config=config["agents"][agent_name])
+        if flat is not None:
+            self.bind(flat)
+
+    def bind(self, flat):
+        """Re-point every nn.Linear parameter at a slice of `flat` (torch order: W1, b1, W2, b2)."""
+        off = 0
+        for l in self.net.modules():
+            if isinstance(l, nn.Linear):
+                for name in ("weight", "bias"):
+                    p = getattr(l, name)
+                    n = p.numel()
+                    view = flat[off:off + n].view(p.shape)
+                    setattr(l, name, nn.Parameter(view, requires_grad=False))
+                    off += n
+        assert off == flat.numel()
+
+    def forward(self, state):
+        return self.net(state)
+
+
+class BaseAgent(nn.Module):
+    def __init__(self, agent_name, env, config):
+        super().__init__()
+        self.state_dim = env.get_state_dim()
+        self.action_dim = env.get_action_dim()
+        agent_config = config["agents"][agent_name]
+        self.train_episodes = agent_config["train_episodes"]
+        self.test_episodes = agent_config["test_episodes"]
+        self.init_episodes = agent_config["init_episodes"]
+        self.rb_size = agent_config["rb_size"]
+        self.same_action_num = agent_config["same_action_num"]
+        self.print_rate = agent_config["print_rate"]
+        self.early_out_num = agent_config["early_out_num"]
+        self.early_out_virtual_diff = agent_config["early_out_virtual_diff"]
+        self.render_env = config["render_env"]
+        self.device = config["device"]
+
+
+class DDQN(BaseAgent):
+    def __init__(self, env, config, icm=False):
+        self.agent_name = "ddqn"
+        super().__init__(agent_name=self.agent_name, env=env, config=config)
+        if icm:
+            raise NotImplementedError("the ICM baseline branch (models/icm_baseline.py) is outside the hot path")
+        c = config["agents"][self.agent_name]
+        self.full_config = config
+        self.batch_size = c["batch_size"]
+        self.rb_size = c["rb_size"]
+        self.gamma = c["gamma"]
+        self.lr = c["lr"]
+        self.tau = c["tau"]
+        self.eps = c["eps_init"]
+        self.eps_init = c["eps_init"]
+        self.eps_min = c["eps_min"]
+        self.eps_decay = c["eps_decay"]
+        self.hidden_size = int(c["hidden_size"])
+        if int(c.get("hidden_layer", 1)) > 1:
+            raise NotImplementedError("Q-nets with hidden_layer > 1 are outside the compiled kernel set")
+        if int(c.get("same_action_num", 1)) != 1:
+            raise NotImplementedError("same_action_num != 1 is outside the compiled kernel set")
+        self._act_id = ACT_IDS[str(c["activation_fn"])]
+        self._env_name = config["env_name"]
+        dev = _cuda_device()
+        # torch-default initialised nets (models/model_utils.py:31,38), then flattened onto the device
+        init = Critic_DQN(self.state_dim, self.action_dim, self.agent_name, config)
+        flat = torch.cat([p.detach().reshape(-1) for p in init.parameters()]).float()
+        self._theta = flat.to(dev).contiguous()
+        self._target = self._theta.clone()
+        self.model = Critic_DQN(self.state_dim, self.action_dim, self.agent_name, config, flat=self._theta)
+        self.model_target = Critic_DQN(self.state_dim, self.action_dim, self.agent_name, config, flat=self._target)
+        self.reset_optimizer()
+        self.it = 0
+        self.icm = None
+        self._seed = random.getrandbits(32)
+        self._runs = 0
+        self.step_budget = 0   # cap on training env steps per train() call (0: none)
+
+    # ---------------------------------------------------------------------------------------------------
+    def _lane_cfg(self, env, test_env, train_episodes, final_test, time_remaining):
+        kind, theta, fields = env.kernel_env() if isinstance(env, EnvWrapper) else (ENV_REAL, None, {})
+        c = LaneCfg()
+        c.sd, c.ad = self.state_dim, self.action_dim
+        c.env_kind = kind
+        c.real_env = REAL_ENV_IDS[self._env_name]
+        c.env_hidden = int(fields.get("env_hidden", 0))
+        c.env_act = int(fields.get("env_act", ACT_IDS["identity"]))
+        for i, sl in enumerate(fields.get("env_slope", [0.01] * 3)):
+            c.env_slope[i] = sl
+        c.rn_type = int(fields.get("rn_type", 0))
+        c.q_hidden, c.q_act = self.hidden_size, self._act_id
+        c.batch_size, c.rb_size = int(self.batch_size), int(self.rb_size)
+        c.train_episodes, c.test_episodes, c.init_episodes = int(train_episodes), int(self.test_episodes), int(self.init_episodes)
+        c.max_steps = int(env.max_episode_steps())
+        c.early_out_num = int(self.early_out_num)
+        c.use_test_env = 1 if test_env is not None else 0
+        c.final_test = 1 if final_test else 0
+        budget = int(self.step_budget)
+        if time_remaining < 1e8:
+            t_budget = max(int(time_remaining * STEPS_PER_SECOND), 0)
+            budget = t_budget if budget == 0 else min(budget, t_budget)
+            budget = max(budget, 1)
+        c.step_budget = budget
+        c.gamma, c.lr, c.tau = float(self.gamma), float(self.lr), float(self.tau)
+        c.eps_init, c.eps_min, c.eps_decay = float(self.eps_init), float(self.eps_min), float(self.eps_decay)
+        c.early_out_virtual_diff = float(self.early_out_virtual_diff)
+        brk = test_env if test_env is not None else env
+        c.solved_reward = float(brk.get_solved_reward())
+        c.beta1, c.beta2, c.adam_eps = 0.9, 0.999, 1e-8
+        return c, theta
+
+    def _run_lane(self, cfg, theta):
+        dev = self._theta.device
+        bufs = ops.InnerLoopBuffers(cfg, 1, 1, dev, want_q_final=True)
+        key = lane_keys(self._seed, self._runs, [0], [0], [0])
+        self._runs += 1
+        th = None if theta is None else theta.to(dev).contiguous()[None]
+        ops.inner_loop_run(bufs, cfg, th, None, ops.keys_tensor(key, dev), q_init=self._theta[None].contiguous())
+        torch.cuda.current_stream().synchronize()
+        return bufs, bufs.results()[0]
+
+    def _replay_from_ring(self, bufs, cfg, n_rows):
+        """The kernel's HBM replay ring (slot 0) as the reference's ReplayBuffer object."""
+        sd = cfg.sd
+        rowf = 2 * sd + 4
+        rb = ReplayBuffer(state_dim=sd, action_dim=1, device=self.device, max_size=int(cfg.rb_size))
+        plan = ops.inner_loop_plan(cfg, 1, 1)
+        n = int(min(n_rows, plan["ring_cap"]))
+        if n <= 0:
+            return rb
+        import ctypes as C
+        from ._abi import load_library
+        off = ops.ring_offset_bytes(cfg, 1, 1)
+        ring = bufs.workspace[off:off + n * rowf * 4].view(torch.float32).reshape(n, rowf).cpu()
+        tail = (sd % 4) == 0
+        off_a = 2 * sd if tail else sd
+        off_s2 = sd if tail else sd + 2
+        rb._alloc(max(n, 1))
+        rb.state[:n] = ring[:, 0:sd]
+        rb.action[:n, 0] = ring[:, off_a]
+        rb.next_state[:n] = ring[:, off_s2:off_s2 + sd]
+        rb.reward[:n, 0] = ring[:, off_a + 1]
+        rb.done[:n, 0] = ring[:, 2 * sd + 2]
+        rb.size = n
+        rb.ptr = n % rb.max_size
+        return rb
+
+    def train(self, env, test_env=None, time_remaining=1e9):
+        """agents/base_agent.py:64-153 as one lane of the fused kernel. The agent's current online weights are the
+        initial weights; the target net starts as a copy and Adam's state starts at zero (a fresh agent per
+        calc_score is the reference's usage, agents/GTN_worker.py:190)."""
+        env.set_agent_params(same_action_num=self.same_action_num, gamma=self.gamma)
+        cfg, theta = self._lane_cfg(env, test_env, self.train_episodes, final_test=False, time_remaining=time_remaining)
+        bufs, out = self._run_lane(cfg, theta)
+        n = int(out["n_episodes"])
+        rewards = bufs.rewards[0, :n].cpu().tolist()
+        lengths = bufs.lengths[0, :n].cpu().tolist()
+        if int(out["timed_out"]):  # time_is_up (agents/base_agent.py:30-47): pad with the worst reward / longest episode
+            print("timeout")
+            if len(rewards) == 0:
+                rewards.append(-1e9)
+            while len(rewards) < self.train_episodes:
+                rewards.append(min(rewards))
+            if len(lengths) == 0:
+                lengths.append(1e9)
+            while len(lengths) < self.train_episodes:
+                lengths.append(max(lengths))
+        self._theta.copy_(bufs.q_final[0])
+        self.it += int(out["learn_iters"])
+        self.last_run = dict(out=out, cfg=cfg)
+        rb = self._replay_from_ring(bufs, cfg, int(out["train_steps"]))
+        env.close()
+        return rewards, lengths, rb
+
+    def test(self, env, time_remaining=1e9):
+        """agents/base_agent.py:155-227: test_episodes greedy rollouts on the (real) env inside the kernel."""
+        if isinstance(env, EnvWrapper) and env.is_virtual_env():
+            raise NotImplementedError("test() on a synthetic env is outside the hot path (the reference tests on the real env)")
+        env.set_agent_params(same_action_num=self.same_action_num, gamma=self.gamma)
+        cfg, _ = self._lane_cfg(env, None, 0, final_test=True, time_remaining=1e9)
+        cfg.env_kind = ENV_REAL
+        bufs, out = self._run_lane(cfg, None)
+        rewards = bufs.test_rewards[0].cpu().tolist()
+        lengths = bufs.test_lengths[0].cpu().tolist()
+        env.close()
+        return rewards, lengths, ReplayBuffer(state_dim=self.state_dim, action_dim=1, device=self.device, max_size=int(1e6))
+
+    # ---- step-by-step API (unit kernels) ------------------------------------------------------------------
+    def _unit_cfg(self):
+        c = LaneCfg()
+        c.sd, c.ad = self.state_dim, self.action_dim
+        c.real_env = REAL_ENV_IDS[self._env_name]
+        c.q_hidden, c.q_act = self.hidden_size, self._act_id
+        c.batch_size = int(self.batch_size)
+        c.gamma, c.lr, c.tau = float(self.gamma), float(self.lr), float(self.tau)
+        c.beta1, c.beta2, c.adam_eps = 0.9, 0.999, 1e-8
+        return c
+
+    def learn(self, replay_buffer, env, episode):
+        self.it += 1
+        states, actions, next_states, rewards, dones = replay_buffer.sample(self.batch_size)
+        rows = torch.cat([states.reshape(self.batch_size, -1).float(), actions.reshape(self.batch_size, 1).float(),
+                          next_states.reshape(self.batch_size, -1).float(), rewards.reshape(self.batch_size, 1).float(),
+                          dones.reshape(self.batch_size, 1).float()], dim=1)
+        dev = self._theta.device
+        loss = ops.td_update(self._unit_cfg(), self._theta[None], self._target[None], self._adam_m[None], self._adam_v[None],
+                             self._adam_t, rows.to(dev).contiguous()[None])
+        return loss[0]
+
+    def _greedy(self, state):
+        dev = self._theta.device
+        s = torch.as_tensor(state, dtype=torch.float32).reshape(1, -1).to(dev)
+        _, am = ops.qnet_forward(self._unit_cfg(), self._theta[None], s)
+        return am.to(torch.int64).cpu()
+
+    def select_train_action(self, state, env, episode):
+        if random.random() < self.eps:
+            return env.get_random_action()
+        return self._greedy(state)
+
+    def select_test_action(self, state, env):
+        return self._greedy(state)
+
+    def update_parameters_per_episode(self, episode):
+        if episode == 0:
+            self.eps = self.eps_init
+        else:
+            self.eps *= self.eps_decay
+            self.eps = max(self.eps, self.eps_min)
+
+    def reset_optimizer(self):
+        self._adam_m = torch.zeros_like(self._theta)
+        self._adam_v = torch.zeros_like(self._theta)
+        self._adam_t = torch.zeros(1, dtype=torch.int32, device=self._theta.device)
+
+
+def vary_hyperparameters(agent_cfg, rng):
+    """Sampling distribution of agents/DDQN_vary.py:26-59 (ConfigSpace 0.4.13 semantics): lr log-uniform on
+    [lr/3, 3 lr]; batch_size and hidden_size log-uniform integers on [int(x/3), int(3x)]; hidden_layer uniform on
+    {L-1, L, L+1}.  `rng`: numpy RandomState. Returns a modified copy."""
+    out = dict(agent_cfg)
+
+    def log_int(lo, hi):
+        lo_f, hi_f = math.log(lo - 0.49999), math.log(hi + 0.49999)
+        return int(min(max(int(round(math.exp(lo_f + (hi_f - lo_f) * rng.random_sample()))), lo), hi))
+    lr, bs, hs, hl = agent_cfg["lr"], agent_cfg["batch_size"], agent_cfg["hidden_size"], agent_cfg["hidden_layer"]
+    out["lr"] = float(math.exp(math.log(lr / 3) + (math.log(lr * 3) - math.log(lr / 3)) * rng.random_sample()))
+    out["batch_size"] = log_int(int(bs / 3), int(bs * 3))
+    out["hidden_size"] = log_int(int(hs / 3), int(hs * 3))
+    out["hidden_layer"] = int(rng.randint(hl - 1, hl + 2))
+    return out
+
+
+class DDQN_vary(DDQN):
+    """agents/DDQN_vary.py: DDQN with sampled lr / batch_size / hidden_size / hidden_layer."""
+    _rng = np.random.RandomState()
+
+    def __init__(self, env, config, icm=False):
+        self.agent_name = 'ddqn'
+        if config["agents"]["ddqn_vary"]["vary_hp"]:
+            config_mod = copy.deepcopy(config)
+            config_mod["agents"]["ddqn"] = vary_hyperparameters(config_mod["agents"]["ddqn"], self._rng)
+            # hidden_layer 0 and 1 build the same net (models/model_utils.py:34 loops hidden_layer-1 times)
+            if config_mod["agents"]["ddqn"]["hidden_layer"] == 0:
+                config_mod["agents"]["ddqn"]["hidden_layer"] = 1
+        else:
+            config_mod = config
+        print("full config: ", config_mod['agents'][self.agent_name])
+        super().__init__(env=env, config=config_mod, icm=icm)
+
+
+_OUTSIDE_HOT_PATH = {"td3", "td3_icm", "td3_vary", "td3_icm_vary", "ppo", "ppo_icm", "duelingddqn", "duelingddqn_icm",
+                     "duelingddqn_vary", "duelingddqn_icm_vary", "td3_discrete_vary", "ql", "ql_cb", "sarsa", "sarsa_cb",
+                     "ddqn_icm", "ddqn_icm_vary"}
+
+
+def select_agent(config, agent_name):
+    """agents/agent_utils.py:15-66."""
+    env_factory = EnvFactory(config)
+    dummy_env = env_factory.generate_real_env(print_str='Select Agent: ')
+    agent_name = agent_name.lower()
+    if agent_name == "ddqn":
+        return DDQN(env=dummy_env, config=config)
+    if agent_name == "ddqn_vary":
+        return DDQN_vary(env=dummy_env, config=config)
+    if agent_name in _OUTSIDE_HOT_PATH:
+        raise NotImplementedError("RL agent %r is outside the B200 hot path (DDQN / DDQN_vary are built)" % agent_name)
+    raise NotImplementedError("Unknownn RL agent")

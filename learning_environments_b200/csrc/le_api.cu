@@ -399,8 +399,8 @@ int64_t le_inner_loop_workspace_bytes(const le_lane_cfg* cfg, int n_lanes, int n
 
 int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* cfg_host0, const float* env_theta_dev, int n_env,
                       const int32_t* env_index_dev, const uint32_t* keys_dev, const float* q_init_dev, float* q_final_dev, int n_lanes,
-                      le_lane_out* out_dev, double* rewards_dev, int32_t* lengths_dev, double* test_rewards_dev, void* workspace_dev,
-                      int64_t workspace_bytes, const le_trace* trace_host, int trace_lane, void* stream) {
+                      le_lane_out* out_dev, double* rewards_dev, int32_t* lengths_dev, double* test_rewards_dev, int32_t* test_lengths_dev,
+                      void* workspace_dev, int64_t workspace_bytes, const le_trace* trace_host, int trace_lane, void* stream) {
     if (!cfg_dev || !cfg_host0 || !keys_dev || !out_dev || !rewards_dev || !lengths_dev || !test_rewards_dev || !workspace_dev ||
         (n_cfg != 1 && n_cfg != n_lanes)) {
         le_set_error("le_inner_loop_run: bad arguments (n_cfg must be 1 or n_lanes; no NULL outputs)");
@@ -437,7 +437,7 @@ int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* 
     P.env_index = env_index_dev; P.keys = keys_dev;
     P.q_init = q_init_dev; P.q_final = q_final_dev;
     P.q_stride = c->q_hidden * (c->sd + c->ad + 1) + c->ad;
-    P.n_lanes = n_lanes; P.out = out_dev; P.rewards = rewards_dev; P.lengths = lengths_dev; P.test_rewards = test_rewards_dev;
+    P.n_lanes = n_lanes; P.out = out_dev; P.rewards = rewards_dev; P.lengths = lengths_dev; P.test_rewards = test_rewards_dev; P.test_lengths = test_lengths_dev;
     P.rew_stride = c->train_episodes > 0 ? c->train_episodes : 1;
     P.test_stride = c->test_episodes;
     P.rings = (float*)(ws + pl.off_rings); P.ring_stride = pl.ring_stride_f; P.ring_cap = pl.ring_cap;
@@ -447,7 +447,8 @@ int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* 
     return LE_OK;
 }
 
-int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid, int* slots, int* ring_cap, int* units) {
+int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid, int* slots, int* ring_cap, int* units,
+                       int64_t* ring_offset_bytes) {
     Plan pl;
     int rc = make_plan(cfg, n_lanes, n_env, &pl);
     if (rc != LE_OK) return rc;
@@ -455,6 +456,7 @@ int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid
     if (slots) *slots = pl.slots;
     if (ring_cap) *ring_cap = pl.ring_cap;
     if (units) *units = pl.ops->units;
+    if (ring_offset_bytes) *ring_offset_bytes = pl.off_rings;
     return LE_OK;
 }
 
@@ -501,7 +503,7 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
     auto dp = [&](size_t i) -> char* { return segs[i].bytes ? arena + segs[i].off : nullptr; };
     rc = le_inner_loop_run((const le_lane_cfg*)dp(i_cfg), n_cfg, c, (const float*)dp(i_th), n_env, (const int32_t*)dp(i_ei),
                            (const uint32_t*)dp(i_key), (const float*)dp(i_qi), (float*)dp(i_qf), n_lanes, (le_lane_out*)dp(i_out),
-                           (double*)dp(i_rw), (int32_t*)dp(i_ln), (double*)dp(i_tr), arena + off_ws, pl.total_bytes, nullptr, 0, st);
+                           (double*)dp(i_rw), (int32_t*)dp(i_ln), (double*)dp(i_tr), nullptr, arena + off_ws, pl.total_bytes, nullptr, 0, st);
     if (rc == LE_OK) {
         for (auto& s : segs)
             if (s.dst_host && s.bytes) {

@@ -17,7 +17,7 @@ struct RunParams {
     const float* q_init; float* q_final; int q_stride;
     int n_lanes;
     le_lane_out* out;
-    double* rewards; int32_t* lengths; double* test_rewards;
+    double* rewards; int32_t* lengths; double* test_rewards; int32_t* test_lengths;
     int rew_stride, test_stride;
     float* rings; int64_t ring_stride; int ring_cap;  // one replay ring per resident warp slot
     int* work_counter;
@@ -79,7 +79,7 @@ struct FusedLane {
     // BaseAgent.test: greedy rollouts on the real env, one episode per thread, weights broadcast from smem.
     static __device__ __forceinline__ double run_test(const Core& core, float* smem, const le_lane_cfg& c, float slope,
                                                       uint32_t k0, uint32_t k1, int test_call, int lane,
-                                                      double* ep_out /* [test_episodes] or nullptr */, int64_t& test_steps) {
+                                                      double* ep_out /* [test_episodes] or nullptr */, int32_t* len_out, int64_t& test_steps) {
         constexpr int PUP = SW::PUP;
         __syncwarp();
 #pragma unroll
@@ -104,6 +104,7 @@ struct FusedLane {
             real_obs<SD>(c.real_env, st, obs);
             int elapsed = 0;
             float ep_rew = 0.f;
+            int ep_steps = 0;
             bool running = active;
             for (int t = 0; t < c.max_steps; ++t) {
                 if (!__any_sync(LE_FULL_MASK, running)) break;
@@ -127,12 +128,14 @@ struct FusedLane {
                     real_step<SD>(c.real_env, c.max_steps, st, elapsed, act, obs, r, d);
                     ep_rew += r;
                     steps += 1;
+                    ep_steps += 1;
                     if (d > 0.5f) running = false;
                 }
             }
             if (active) {
                 sum += (double)ep_rew;
                 if (ep_out) ep_out[ep] = (double)ep_rew;
+                if (len_out) len_out[ep] = ep_steps;
             }
         }
         sum = warp_allreduce_sum(sum);
@@ -284,7 +287,7 @@ struct FusedLane {
             }
             // ---- episode bookkeeping (agents/base_agent.py:131-148)
             double ep_value;
-            if (c.use_test_env) ep_value = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, nullptr, test_steps);
+            if (c.use_test_env) ep_value = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, nullptr, nullptr, test_steps);
             else ep_value = (double)ep_rew;
             if (lane == 0) { lengths[n_ep] = ep_len; rewards[n_ep] = ep_value; }
             n_ep += 1;
@@ -301,7 +304,9 @@ struct FusedLane {
             }
         }
         double score = 0.0;
-        if (c.final_test) score = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, test_rewards, test_steps);
+        if (c.final_test)
+            score = run_test(core, smem, c, ls.slope, k0, k1, test_calls++, lane, test_rewards,
+                             P.test_lengths ? P.test_lengths + (int64_t)lane_id * P.test_stride : nullptr, test_steps);
         if (P.q_final) core.store_net(P.q_final + (int64_t)lane_id * P.q_stride, H, lane, 0);
         if (lane == 0) {
             le_lane_out o;

@@ -116,10 +116,14 @@ def td_update(cfg, q_theta, q_target, adam_m, adam_v, adam_t, rows):
 
 # ---------------------------------------------------------------------------------------------------------
 def inner_loop_plan(cfg, n_lanes, n_env=1):
-    g, s, r, u = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    check(_lib().le_inner_loop_plan(C.byref(cfg), C.c_int(n_lanes), C.c_int(n_env), C.byref(g), C.byref(s), C.byref(r), C.byref(u)),
-          "le_inner_loop_plan")
-    return dict(grid=g.value, slots=s.value, ring_cap=r.value, units=u.value)
+    g, s, r, u, o = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(_lib().le_inner_loop_plan(C.byref(cfg), C.c_int(n_lanes), C.c_int(n_env), C.byref(g), C.byref(s), C.byref(r), C.byref(u),
+                                    C.byref(o)), "le_inner_loop_plan")
+    return dict(grid=g.value, slots=s.value, ring_cap=r.value, units=u.value, ring_offset_bytes=o.value)
+
+
+def ring_offset_bytes(cfg, n_lanes, n_env=1):
+    return inner_loop_plan(cfg, n_lanes, n_env)["ring_offset_bytes"]
 
 
 def lane_out_dtype():
@@ -141,6 +145,7 @@ class InnerLoopBuffers(object):
         self.rewards = torch.zeros((n_lanes, rs), dtype=_F64, device=device)
         self.lengths = torch.zeros((n_lanes, rs), dtype=_I32, device=device)
         self.test_rewards = torch.zeros((n_lanes, cfg.test_episodes), dtype=_F64, device=device)
+        self.test_lengths = torch.zeros((n_lanes, cfg.test_episodes), dtype=_I32, device=device)
         self.q_final = torch.zeros((n_lanes, cfg.q_params()), dtype=_F32, device=device) if want_q_final else None
         self.cfg_dev = torch.zeros((n_cfg, C.sizeof(LaneCfg)), dtype=torch.uint8, device=device)
         self.trace = None
@@ -185,7 +190,7 @@ def inner_loop_run(bufs, cfgs, env_theta, env_index, keys, q_init=None, trace_la
         _ptr(bufs.cfg_dev), C.c_int(n_cfg), C.byref(cfg0), _ptr(env_theta) if env_theta is not None else None, C.c_int(n_env),
         _ptr(env_index) if env_index is not None else None, _ptr(keys), _ptr(q_init) if q_init is not None else None,
         _ptr(bufs.q_final) if bufs.q_final is not None else None, C.c_int(bufs.n_lanes), _ptr(bufs.out), _ptr(bufs.rewards),
-        _ptr(bufs.lengths), _ptr(bufs.test_rewards), _ptr(bufs.workspace), C.c_int64(bufs.workspace.numel()),
+        _ptr(bufs.lengths), _ptr(bufs.test_rewards), _ptr(bufs.test_lengths), _ptr(bufs.workspace), C.c_int64(bufs.workspace.numel()),
         C.byref(tr) if tr is not None else None, C.c_int(trace_lane), _stream()), "le_inner_loop_run")
 
 

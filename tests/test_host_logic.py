@@ -1,0 +1,201 @@
+"""Host-side logic of the drop-in API on CPU (no CUDA calls): config mapping, helpers, error behaviour,
+GTN_Master with an oracle-backed evaluator, and the world_size-2 path over gloo."""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from learning_environments_b200 import agents, config as le_config, default_configs, envs, gtn, nes, utils
+from learning_environments_b200._abi import ENV_RN, ENV_SE, LaneCfg
+from tests.helpers import cfg_from_bytes, load_golden
+from tests.oracle_backend import OracleEvaluator, patch_master_for_cpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_default_configs_map_to_the_reference_lane_cfg():
+    """default_configs + config.lane_cfg reproduce the le_lane_cfg generated from the reference's YAML files."""
+    for tag, name, kind, over in (("cartpole_se", "cartpole_syn_env", ENV_SE, dict(train_episodes=5, test_episodes=3, init_episodes=1)),
+                                  ("acrobot_se", "acrobot_syn_env", ENV_SE, dict(train_episodes=4, test_episodes=2, init_episodes=1)),
+                                  ("cartpole_rn", "cartpole_reward_env", ENV_RN, dict(train_episodes=12, test_episodes=1, init_episodes=2))):
+        g = load_golden("trajectory_%s.npz" % tag)
+        want = cfg_from_bytes(g["cfg"])
+        d = default_configs.get(name)
+        d["agents"]["ddqn"].update(over)
+        got = le_config.lane_cfg(d, "ddqn", kind, use_test_env=True, final_test=True)
+        assert bytes(got) == bytes(want), tag
+
+
+def test_lane_cfg_rejects_shapes_outside_the_kernel_set():
+    d = default_configs.get("cartpole_syn_env")
+    d["agents"]["ddqn"]["hidden_layer"] = 2
+    with pytest.raises(NotImplementedError):
+        le_config.lane_cfg(d, "ddqn", ENV_SE)
+    d = default_configs.get("cartpole_syn_env")
+    d["env_name"] = "Pendulum-v0"
+    d["envs"]["Pendulum-v0"] = d["envs"]["CartPole-v0"]
+    with pytest.raises(NotImplementedError):
+        le_config.lane_cfg(d, "ddqn", ENV_SE)
+
+
+def test_env_factory_state_dict_keys_and_theta_roundtrip():
+    f = envs.EnvFactory(default_configs.get("cartpole_syn_env"))
+    v = f.generate_virtual_env()
+    assert v.is_virtual_env() and v.get_state_dim() == 4 and v.get_action_dim() == 2 and v.max_episode_steps() == 200
+    keys = sorted(v.state_dict().keys())
+    assert keys == sorted("env.%s.%d.%s" % (n, i, p) for n in ("state_net", "reward_net", "done_net") for i in (0, 2)
+                          for p in ("weight", "bias"))
+    th = v.env.theta()
+    assert th.numel() == 2247
+    envs.set_linear_theta(v.env, th * 2)
+    assert torch.equal(v.env.theta(), th * 2)
+    r = envs.EnvFactory(default_configs.get("cartpole_reward_env")).generate_reward_env()
+    assert not r.is_virtual_env() and r.env.theta().numel() == 385 and "env.reward_net.1.weight" in r.state_dict()
+    a = envs.EnvFactory(default_configs.get("acrobot_syn_env")).generate_virtual_env()
+    assert a.env.theta().numel() == 6354 and a.get_solved_reward() == -100.0
+    for t in (3, 9):
+        c = default_configs.get("cartpole_reward_env")
+        c["envs"]["CartPole-v0"]["reward_env_type"] = t
+        if t == 9:
+            with pytest.raises(NotImplementedError):
+                envs.EnvFactory(c).generate_reward_env()
+
+
+def test_average_meter_and_one_hot_match_reference_semantics():
+    m = utils.AverageMeter("x")
+    for v in (1.0, 2.0, 3.0, 10.0):
+        m.update(v, print_rate=10 ** 9)
+    assert abs(m.get_mean(2) - 6.5 / (1 + 1e-9 / 2)) < 1e-6 and abs(m.get_mean_last(2) - 1.5) < 1e-6
+    assert m.get_mean(10) == sum([1.0, 2.0, 3.0, 10.0]) / (4 + 1e-9)
+    assert utils.to_one_hot_encoding(torch.tensor([1.0]), 3).tolist() == [0, 1, 0]
+    assert utils.to_one_hot_encoding(torch.tensor([0.0, 2.0]), 3).tolist() == [[1, 0, 0], [0, 0, 1]]
+    assert utils.from_one_hot_encoding(torch.tensor([0.0, 0.0, 1.0])).tolist() == [2]
+
+
+def test_replay_buffer_ring_semantics():
+    rb = utils.ReplayBuffer(state_dim=2, action_dim=1, device="cpu", max_size=5)
+    for i in range(7):
+        rb.add(torch.tensor([i, i], dtype=torch.float32), torch.tensor([i % 2]), torch.tensor([i + 1.0, i + 1.0]),
+               torch.tensor(float(i)), torch.tensor(0.0))
+    assert rb.size == 5 and rb.ptr == 2
+    assert rb.state[:5, 0].tolist() == [5.0, 6.0, 2.0, 3.0, 4.0]      # rows 0,1 overwritten by transitions 5,6
+    s, a, s2, r, d = rb.sample(64)
+    assert s.shape == (64, 2) and set(r.reshape(-1).tolist()) <= {2.0, 3.0, 4.0, 5.0, 6.0}
+    assert rb.get_all()[0].shape == (5, 2)
+
+
+@pytest.mark.reference
+def test_replay_buffer_and_average_meter_against_the_reference_classes():
+    from oracle import ref_harness as rh
+    ref = rh.import_reference()["utils"]
+    a, b = utils.ReplayBuffer(3, 1, "cpu", max_size=4), ref.ReplayBuffer(3, 1, "cpu", max_size=4)
+    rng = np.random.RandomState(0)
+    for i in range(9):
+        args = [torch.from_numpy(rng.rand(3).astype(np.float32)), torch.tensor([float(i % 2)]),
+                torch.from_numpy(rng.rand(3).astype(np.float32)), torch.tensor([float(i)]), torch.tensor(float(i % 3 == 0))]
+        a.add(*args)
+        b.add(*args)
+        assert (a.ptr, a.size) == (b.ptr, b.size)
+    for x, y in zip(a.get_all(), b.get_all()):
+        assert torch.equal(x, y)
+    ma, mb = utils.AverageMeter(""), ref.AverageMeter("")
+    for v in rng.rand(25):
+        ma.update(v, print_rate=10 ** 9)
+        mb.update(v, print_rate=10 ** 9)
+        assert ma.get_mean(10) == mb.get_mean(10) and ma.get_mean_last(10) == mb.get_mean_last(10)
+
+
+def test_vary_hyperparameters_ranges():
+    base = default_configs.get("cartpole_syn_env")["agents"]["ddqn"]
+    rng = np.random.RandomState(0)
+    seen_layers = set()
+    for _ in range(300):
+        v = agents.vary_hyperparameters(base, rng)
+        assert base["lr"] / 3 <= v["lr"] <= base["lr"] * 3
+        assert int(199 / 3) <= v["batch_size"] <= 597 and int(57 / 3) <= v["hidden_size"] <= 171
+        seen_layers.add(v["hidden_layer"])
+    assert seen_layers == {0, 1, 2}
+
+
+def test_select_agent_error_behaviour_without_gpu():
+    cfg = default_configs.get("cartpole_syn_env")
+    with pytest.raises(NotImplementedError, match="Unknownn RL agent"):
+        agents.select_agent(cfg, "nonsense")
+    with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
+        agents.select_agent(cfg, "TD3")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA device is required"):      # fails loudly: no CPU fallback
+            agents.select_agent(cfg, "DDQN")
+
+
+def _small_gtn_config(workers=4, iters=2):
+    cfg = default_configs.get("cartpole_syn_env")
+    cfg["agents"]["gtn"].update(num_workers=workers, max_iterations=iters)
+    cfg["agents"]["ddqn"].update(train_episodes=2, test_episodes=2, init_episodes=1)
+    return cfg
+
+
+def test_gtn_master_generation_logic_with_oracle_backend(monkeypatch, tmp_path):
+    from oracle import nes as onese
+    patch_master_for_cpu(monkeypatch)
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    cfg = _small_gtn_config()
+    m = gtn.GTN_Master(cfg, seed=77, evaluator_cls=OracleEvaluator, verbose=False)
+    theta0 = m.theta.clone()
+    mean_score, mean_list, model_name = m.run()                       # 3-tuple, as agents/GTN_master.py:114
+    assert len(mean_list) == 2 and model_name.endswith(".pt") and np.isfinite(mean_score)
+    assert not torch.equal(m.theta, theta0)
+    assert torch.equal(envs.linear_theta(m.synthetic_env_orig.env), m.theta)     # the env object carries the new theta
+    # replay generation 1's update by hand from the recorded scores
+    w = onese.score_transform(m.score_list, m.score_orig_list, 3)
+    assert np.array_equal(np.asarray(m.score_transform_list), w)
+    assert all(s in (-1.0, 1.0) for s in m.sign_list)
+    # checkpoint rule: SE models are saved only above solved_reward (195) -> nothing saved for random SEs
+    assert not os.path.exists(model_name)
+    m.best_score = -1e9
+    m.real_env.env.solved_reward = -1e9
+    assert m.save_good_model(10.0) is True and os.path.exists(model_name)
+    ck = torch.load(model_name, weights_only=False)
+    assert set(ck.keys()) == {"model", "config"} and "env.state_net.0.weight" in ck["model"]
+
+
+def test_gtn_master_unknown_options_raise_like_the_reference(monkeypatch, tmp_path):
+    patch_master_for_cpu(monkeypatch)
+    monkeypatch.chdir(tmp_path)
+    cfg = _small_gtn_config()
+    cfg["agents"]["gtn"]["synthetic_env_type"] = 2
+    with pytest.raises(NotImplementedError, match="Unknown synthetic_env_type"):
+        gtn.GTN_Master(cfg, evaluator_cls=OracleEvaluator, verbose=False)
+    cfg = _small_gtn_config()
+    cfg["agents"]["gtn"]["score_transform_type"] = 11
+    m = gtn.GTN_Master(cfg, seed=1, evaluator_cls=OracleEvaluator, verbose=False)
+    m.score_list, m.score_orig_list = [1.0, 2.0, 3.0, 4.0], [1.0] * 4
+    with pytest.raises(ValueError, match="Unknown rank transform type"):
+        m.score_transform()
+
+
+@pytest.mark.parametrize("mode", ["replicated", "allreduce"])
+def test_gtn_master_two_ranks_gloo_matches_single_rank(tmp_path, mode):
+    """world_size 2 over gloo: block-sharded members, all-gather of scores, identical theta on both ranks and
+    equal (replicated: bit-exact; allreduce: fp32 reassociation) to the single-process result."""
+    script = os.path.join(ROOT, "tests", "gloo_gtn_worker.py")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out1 = tmp_path / "single.npy"
+    subprocess.check_call([sys.executable, script, "--mode", mode, "--out", str(out1)], env=env, cwd=str(tmp_path))
+    out2 = tmp_path / "dist"
+    port = 29000 + os.getpid() % 2000
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                           "127.0.0.1", "--master-port", str(port), script, "--mode", mode, "--out", str(out2)], env=env,
+                          cwd=str(tmp_path), timeout=600)
+    single = np.load(out1)
+    r0, r1 = np.load(str(out2) + ".rank0.npy"), np.load(str(out2) + ".rank1.npy")
+    assert np.array_equal(r0, r1)
+    if mode == "replicated":
+        assert np.array_equal(r0, single)
+    else:
+        assert np.allclose(r0, single, rtol=1e-5, atol=1e-7)
