@@ -330,7 +330,8 @@ def main():
             "gpu_launches": 3 * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / ffma_peak if ffma_peak else None, "traffic": None,
+                         "frac": achieved / ffma_peak if ffma_peak else None,
+                         "traffic": _ncu_traffic(steps_all / world / max(args.steps, 1)),
                          "flop_per_env_step": F, "peak_source": "le_bench_ffma microbenchmark in this run (FP32 FFMA; "
                                                                 "MEASURED_PEAKS.json has no FP32 figure)",
                          "hbm": {"algorithmic_bytes_per_env_step": (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4,
@@ -348,6 +349,21 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _ncu_traffic(env_steps_per_launch):
+    """DRAM bytes per launch of the fused kernel from the committed `ncu --set full` capture (profiles/), scaled to
+    this run's env steps per launch; None if no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            t = json.load(f)
+        return t["dram_bytes_per_env_step"] * env_steps_per_launch
+    except Exception:
+        return None
 
 
 def _measured_hbm():
