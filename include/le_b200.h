@@ -46,6 +46,10 @@ extern "C" {
 #define LE_ENV_RN 1   /* envs/reward_env.py RewardEnv over the real env       */
 #define LE_ENV_REAL 2 /* the gym env itself (envs/env_wrapper.py:51-70)       */
 
+/* Q-network kinds */
+#define LE_Q_DQN 0
+#define LE_Q_DUELING 1
+
 /* real environments (gym 0.17.3 classic_control, restated: SURVEY.md Appendix A) */
 #define LE_REAL_CARTPOLE 0
 #define LE_REAL_ACROBOT 1
@@ -57,6 +61,10 @@ extern "C" {
  *                     P_se = 3*H*(sd+ad+1) + H*(sd+2) + sd+2               (CartPole 2247, Acrobot 6354)
  *   RN  (LE_ENV_RN):  reward_net: W1[H][sd], b1[H], W2[1][H], b2[1]        P_rn = H*(sd+2)+1  (385)
  *   Q   (Critic_DQN): W1[H][sd], b1[H], W2[ad][H], b2[ad]                  P_q  = H*(sd+ad+1)+ad (401)
+ *       general form (q_layers = L >= 1): Linear(sd,H), [Linear(H,H)] x (L-1), Linear(H,ad), each W[out][in] then b[out]
+ *   Q   (Critic_DuelingDQN): feature_stream = Linear(sd,H), [Linear(H,H)] x (L-1), Linear(H,fd) (no activation after
+ *       the last); value_stream = Linear(fd,fd), Linear(fd,1); advantage_stream = Linear(fd,fd), Linear(fd,ad);
+ *       q = V + (A - mean over the whole batch of A)                       (CartPole yaml: 11 528 parameters)
  * PReLU slopes are not part of theta (never perturbed/updated: agents/GTN_worker.py:156-163 touches
  * nn.Linear only); they travel in le_lane_cfg.env_slope.
  */
@@ -85,6 +93,10 @@ typedef struct le_lane_cfg {
     double gamma, lr, tau, eps_init, eps_min, eps_decay; /* agents/DDQN.py:24-32                       */
     double early_out_virtual_diff, solved_reward;        /* agents/base_agent.py:23, env config        */
     double beta1, beta2, adam_eps;                       /* torch.optim.Adam defaults .9/.999/1e-8     */
+    int32_t q_kind;         /* LE_Q_DQN (models/actor_critic.py:84-91) | LE_Q_DUELING (:94-122)                */
+    int32_t q_layers;       /* hidden_layer of the Q-net / feature stream (0 and 1 build the same net)         */
+    int32_t q_feature_dim;  /* Critic_DuelingDQN feature_dim (heads: fd -> fd -> {1, ad})                      */
+    int32_t reserved0;
 } le_lane_cfg;
 
 /* Per-lane results (what train()/test() return, as arrays). */

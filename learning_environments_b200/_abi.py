@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", os.environ.get("LE_LIB_NAME", "lible_b200
 
 ACT_IDS = {"tanh": 0, "relu": 1, "leakyrelu": 2, "prelu": 3, "identity": 4}
 ENV_SE, ENV_RN, ENV_REAL = 0, 1, 2
+Q_DQN, Q_DUELING = 0, 1
 REAL_CARTPOLE, REAL_ACROBOT = 0, 1
 REAL_ENV_IDS = {"CartPole-v0": REAL_CARTPOLE, "Acrobot-v1": REAL_ACROBOT}
 
@@ -32,6 +33,7 @@ class LaneCfg(C.Structure):
         ("eps_init", C.c_double), ("eps_min", C.c_double), ("eps_decay", C.c_double),
         ("early_out_virtual_diff", C.c_double), ("solved_reward", C.c_double),
         ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
+        ("q_kind", C.c_int32), ("q_layers", C.c_int32), ("q_feature_dim", C.c_int32), ("reserved0", C.c_int32),
     ]
 
     def copy(self):
@@ -58,8 +60,21 @@ class LaneCfg(C.Structure):
             return self.rn_params()
         return 0
 
+    def q_layer_dims(self):
+        """[(in, out), ...] of every nn.Linear of the Q-net in state_dict order."""
+        L = max(int(self.q_layers), 1)
+        H = self.q_hidden
+        if self.q_kind == Q_DQN:
+            return [(self.sd, H)] + [(H, H)] * (L - 1) + [(H, self.ad)]
+        fd = self.q_feature_dim
+        return [(self.sd, H)] + [(H, H)] * (L - 1) + [(H, fd), (fd, fd), (fd, 1), (fd, fd), (fd, self.ad)]
+
     def q_params(self):
-        return self.mlp_params(self.sd, self.q_hidden, self.ad)
+        return sum(i * o + o for i, o in self.q_layer_dims())
+
+    def q_is_register_resident(self):
+        """True when the warp-per-lane register kernel set covers this Q-net (else the general CTA-per-lane kernel)."""
+        return self.q_kind == Q_DQN and self.q_layers <= 1 and self.q_hidden <= 128
 
 
 class LaneOut(C.Structure):

@@ -5,7 +5,7 @@ envs/env_factory.py:45-59 (lists -> float(value[1])), envs/virtual_env.py:11-21,
 """
 import copy
 
-from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, REAL_ENV_IDS, LaneCfg
+from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, Q_DQN, Q_DUELING, REAL_ENV_IDS, LaneCfg
 
 ENV_DIMS = {"CartPole-v0": (4, 2), "Acrobot-v1": (6, 3)}
 
@@ -37,8 +37,8 @@ def lane_cfg(config, agent_name="ddqn", env_kind=ENV_SE, use_test_env=True, fina
     c.real_env = REAL_ENV_IDS[env_name]
     if int(e.get("hidden_layer", 1)) > 1 and env_kind != ENV_REAL:
         raise NotImplementedError("SE/RN nets with hidden_layer > 1 are outside the compiled kernel set")
-    if int(a.get("hidden_layer", 1)) > 1:
-        raise NotImplementedError("Q-nets with hidden_layer > 1 are outside the compiled kernel set")
+    if int(a.get("hidden_layer", 1)) > 2:
+        raise NotImplementedError("Q-nets with hidden_layer > 2 are outside the compiled kernel set")
     if int(a.get("same_action_num", 1)) != 1:
         raise NotImplementedError("same_action_num != 1 is outside the compiled kernel set")
     c.env_hidden = int(e.get("hidden_size", 0))
@@ -48,6 +48,9 @@ def lane_cfg(config, agent_name="ddqn", env_kind=ENV_SE, use_test_env=True, fina
         c.env_slope[i] = slope
     c.rn_type = int(e.get("reward_env_type", 0))
     c.q_hidden = int(a["hidden_size"])
+    c.q_kind = Q_DUELING if agent_name.startswith("duelingddqn") else Q_DQN
+    c.q_layers = max(int(a.get("hidden_layer", 1)), 1)
+    c.q_feature_dim = int(a.get("feature_dim", 0)) if c.q_kind == Q_DUELING else 0
     c.q_act = ACT_IDS[str(a["activation_fn"])]
     if c.q_act not in (ACT_IDS["tanh"], ACT_IDS["relu"], ACT_IDS["leakyrelu"]):
         raise NotImplementedError("Q-net activation %r is outside the compiled kernel set" % a["activation_fn"])

@@ -42,8 +42,10 @@ def linear_params(module):
     return np.concatenate(out).astype(np.float32)
 
 
-def small_config(name, **agent_overrides):
+def small_config(name, agent_name=None, **agent_overrides):
     cfg = rh.load_reference_yaml(name)
+    if agent_name is not None:
+        cfg["agents"].setdefault("gtn", {})["agent_name"] = agent_name
     agent = cfg["agents"]["gtn"]["agent_name"].lower()
     cfg["agents"][agent].update(agent_overrides)
     cfg["agents"][agent]["print_rate"] = 10 ** 9
@@ -113,11 +115,11 @@ def gen_rn_reward(seed):
              yaml=yaml_name, cfg=cfg_bytes(cfg, "ddqn", ENV_RN, gamma=0.99), **out)
 
 
-def gen_td_update(yaml_name, tag, seed, steps=5):
-    """DDQN.learn (agents/DDQN.py:60-95) `steps` times on explicit minibatches."""
+def gen_td_update(yaml_name, tag, seed, steps=5, agent=None, **overrides):
+    """DDQN.learn / DuelingDDQN.learn (agents/DDQN.py:60-95, agents/DuelingDDQN.py:59-94) `steps` times on explicit minibatches."""
     import torch
     mods = rh.import_reference()
-    cfg, agent_name = small_config(yaml_name)
+    cfg, agent_name = small_config(yaml_name, agent, **overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     real_env = fac.generate_real_env()
@@ -149,8 +151,8 @@ def gen_td_update(yaml_name, tag, seed, steps=5):
         thetas.append(linear_params(agent.model))
         targets.append(linear_params(agent.model_target))
     st = agent.optimizer.state_dict()["state"]
-    m = np.concatenate([st[i]["exp_avg"].numpy().reshape(-1) for i in range(4)])
-    v = np.concatenate([st[i]["exp_avg_sq"].numpy().reshape(-1) for i in range(4)])
+    m = np.concatenate([st[i]["exp_avg"].numpy().reshape(-1) for i in range(len(st))])
+    v = np.concatenate([st[i]["exp_avg_sq"].numpy().reshape(-1) for i in range(len(st))])
     np.savez(os.path.join(GOLDEN, "td_update_%s.npz" % tag), q_init=q0, rows=rows, thetas=np.stack(thetas),
              targets=np.stack(targets), losses=np.array(losses, np.float32), adam_m=m, adam_v=v, yaml=yaml_name,
              cfg=cfg_bytes(cfg, agent_name, ENV_RN if "reward_env" in yaml_name else ENV_SE))
@@ -187,11 +189,11 @@ def gen_real_env(seed):
         np.savez(os.path.join(GOLDEN, "real_env_%s.npz" % tag), n_episodes=len(eps), **flat)
 
 
-def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, use_test_env=True):
+def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, use_test_env=True, agent=None):
     """Full BaseAgent.train(+test) of the reference under RNG injection; per-step trace of the first steps."""
     import torch
     mods = rh.import_reference()
-    cfg, agent_name = small_config(yaml_name, **overrides)
+    cfg, agent_name = small_config(yaml_name, agent, **overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     real_env = fac.generate_real_env()
@@ -327,6 +329,9 @@ def main():
     gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole", 4)
     gen_td_update("default_config_acrobot_syn_env.yaml", "acrobot", 5)
     gen_td_update("default_config_cartpole_reward_env.yaml", "cartpole_rn", 6)
+    gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole_dueling", 8, agent="DuelingDDQN")
+    gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")
+    gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)
     gen_real_env(7)
     gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se", 11, (0x1234, 0xABCD), "se",
                    dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)
@@ -336,6 +341,8 @@ def main():
                    dict(train_episodes=12, test_episodes=1, init_episodes=2), trace_cap=300)
     gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se_notest", 14, (0x42, 0x43), "se",
                    dict(train_episodes=8, test_episodes=3, init_episodes=2, early_out_num=2), trace_cap=200, use_test_env=False)
+    gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se_dueling", 15, (0x51, 0x52), "se",
+                   dict(train_episodes=3, test_episodes=2, init_episodes=1), trace_cap=300, agent="DuelingDDQN")
     gen_nes(21)
     print("golden fixtures written to", GOLDEN)
 

@@ -87,7 +87,9 @@ int le_oracle_se_params(const le_lane_cfg* c) {
     return le_oracle_mlp_params(in, H, c->sd) + 2 * le_oracle_mlp_params(in, H, 1);
 }
 int le_oracle_rn_params(const le_lane_cfg* c) { return le_oracle_mlp_params(c->sd, c->env_hidden, 1); }
-int le_oracle_q_params(const le_lane_cfg* c) { return le_oracle_mlp_params(c->sd, c->q_hidden, c->ad); }
+static int is_simple_dqn(const le_lane_cfg* c);
+static int general_q_params(const le_lane_cfg* c);
+int le_oracle_q_params(const le_lane_cfg* c) { return is_simple_dqn(c) ? le_oracle_mlp_params(c->sd, c->q_hidden, c->ad) : general_q_params(c); }
 
 /* VirtualEnv.step (envs/virtual_env.py:43-54): input = cat(one_hot(action), state); three nets. */
 void le_oracle_se_step(const le_lane_cfg* c, const float* theta, const float* state, int action, float* next_state,
@@ -129,12 +131,180 @@ int le_oracle_rn_reward(const le_lane_cfg* c, const float* theta, const float* s
     }
 }
 
+void le_oracle_q_forward_general(const le_lane_cfg* c, const float* th, const float* state, float* q, int* argmax);
 void le_oracle_q_forward(const le_lane_cfg* c, const float* q_theta, const float* state, float* q, int* argmax) {
+    if (!(c->q_kind == LE_Q_DQN && c->q_layers <= 1)) { le_oracle_q_forward_general(c, q_theta, state, q, argmax); return; }
     mlp_forward(q_theta, c->sd, c->q_hidden, c->ad, c->q_act, 0.f, state, q, NULL, NULL);
     int best = 0;
     for (int a = 1; a < c->ad; ++a)
         if (q[a] > q[best]) best = a; /* torch.argmax: first maximal index */
     if (argmax) *argmax = best;
+}
+
+
+/* ------------------------------------------------------------------------------------------------ */
+/* General Q-networks: Critic_DQN with hidden_layer >= 1 and Critic_DuelingDQN (models/actor_critic.py:84-122)  */
+
+typedef struct { int in, out, act, w_off, b_off, y_off; } olayer; /* y_off: offset of the layer output in a row's activation record */
+typedef struct {
+    int kind, nfeat, P, sum_out, sd, ad;
+    olayer feat[4], val[2], adv[2];
+} onet;
+
+static void add_layer(olayer* l, int in, int out, int act, int* p, int* y) {
+    l->in = in; l->out = out; l->act = act; l->w_off = *p; *p += in * out; l->b_off = *p; *p += out; l->y_off = *y; *y += out;
+}
+
+static void build_net(const le_lane_cfg* c, onet* n) {
+    int p = 0, y = 0;
+    const int L = c->q_layers > 1 ? c->q_layers : 1, H = c->q_hidden, act = c->q_act;
+    n->kind = c->q_kind; n->sd = c->sd; n->ad = c->ad; n->nfeat = 0;
+    add_layer(&n->feat[n->nfeat++], c->sd, H, act, &p, &y);
+    for (int i = 1; i < L; ++i) add_layer(&n->feat[n->nfeat++], H, H, act, &p, &y);
+    if (c->q_kind == LE_Q_DQN) {
+        add_layer(&n->feat[n->nfeat++], H, c->ad, LE_ACT_IDENTITY, &p, &y);
+    } else {
+        const int fd = c->q_feature_dim;
+        add_layer(&n->feat[n->nfeat++], H, fd, LE_ACT_IDENTITY, &p, &y); /* no activation after the feature stream */
+        add_layer(&n->val[0], fd, fd, act, &p, &y);
+        add_layer(&n->val[1], fd, 1, LE_ACT_IDENTITY, &p, &y);
+        add_layer(&n->adv[0], fd, fd, act, &p, &y);
+        add_layer(&n->adv[1], fd, c->ad, LE_ACT_IDENTITY, &p, &y);
+    }
+    n->P = p; n->sum_out = y;
+}
+
+static int is_simple_dqn(const le_lane_cfg* c) { return c->q_kind == LE_Q_DQN && c->q_layers <= 1; }
+static int general_q_params(const le_lane_cfg* c) { onet n; build_net(c, &n); return n.P; }
+
+static void layer_fwd(const olayer* l, const float* th, const float* x, float* y) {
+    for (int o = 0; o < l->out; ++o) {
+        float z = th[l->b_off + o];
+        const float* w = th + l->w_off + (size_t)o * l->in;
+        for (int i = 0; i < l->in; ++i) z += w[i] * x[i];
+        y[o] = act_f(l->act, 0.f, z);
+    }
+}
+
+/* one row through the net; acts = the row's activation record [sum_out]; returns pointers to V (or NULL) and A/q */
+static void net_forward_row(const onet* n, const float* th, const float* x, float* acts, const float** v_out, const float** a_out) {
+    const float* in = x;
+    for (int i = 0; i < n->nfeat; ++i) { layer_fwd(&n->feat[i], th, in, acts + n->feat[i].y_off); in = acts + n->feat[i].y_off; }
+    if (n->kind == LE_Q_DQN) { *v_out = NULL; *a_out = in; return; }
+    layer_fwd(&n->val[0], th, in, acts + n->val[0].y_off);
+    layer_fwd(&n->val[1], th, acts + n->val[0].y_off, acts + n->val[1].y_off);
+    layer_fwd(&n->adv[0], th, in, acts + n->adv[0].y_off);
+    layer_fwd(&n->adv[1], th, acts + n->adv[0].y_off, acts + n->adv[1].y_off);
+    *v_out = acts + n->val[1].y_off; *a_out = acts + n->adv[1].y_off;
+}
+
+/* q-values of a batch: DQN -> the output layer; dueling -> V + (A - mean over ALL rows and actions of A) (:121) */
+static void net_forward_batch(const onet* n, const float* th, const float* X, int x_stride, int B, float* acts, float* q) {
+    double dummy = 0.0; (void)dummy;
+    float asum = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float *v, *a;
+        net_forward_row(n, th, X + (size_t)b * x_stride, acts + (size_t)b * n->sum_out, &v, &a);
+        for (int k = 0; k < n->ad; ++k) { q[b * n->ad + k] = a[k]; asum += a[k]; }
+    }
+    if (n->kind == LE_Q_DUELING) {
+        const float mean = asum / (float)(B * n->ad);
+        for (int b = 0; b < B; ++b) {
+            const float v = acts[(size_t)b * n->sum_out + n->val[1].y_off];
+            for (int k = 0; k < n->ad; ++k) q[b * n->ad + k] = v + (q[b * n->ad + k] - mean);
+        }
+    }
+}
+
+static void layer_bwd(const olayer* l, const float* th, float* g, const float* x, const float* y, float* dy /* in: dL/dy, destroyed */,
+                      float* dx /* accumulated into, may be NULL */) {
+    for (int o = 0; o < l->out; ++o) {
+        const float dz = dy[o] * act_grad(l->act, 0.f, y[o], y[o]);  /* relu/leaky: sign(y) == sign(z) */
+        g[l->b_off + o] += dz;
+        float* gw = g + l->w_off + (size_t)o * l->in;
+        const float* w = th + l->w_off + (size_t)o * l->in;
+        for (int i = 0; i < l->in; ++i) { gw[i] += dz * x[i]; if (dx) dx[i] += dz * w[i]; }
+    }
+}
+
+void le_oracle_q_forward_general(const le_lane_cfg* c, const float* th, const float* state, float* q, int* argmax) {
+    onet n; build_net(c, &n);
+    float* acts = (float*)malloc(sizeof(float) * n.sum_out);
+    net_forward_batch(&n, th, state, c->sd, 1, acts, q);
+    int best = 0;
+    for (int a = 1; a < c->ad; ++a) if (q[a] > q[best]) best = a;
+    if (argmax) *argmax = best;
+    free(acts);
+}
+
+static float td_update_general(const le_lane_cfg* c, float* th, float* thT, float* m, float* v, int32_t* adam_t, const float* rows, int B) {
+    onet n; build_net(c, &n);
+    const int sd = c->sd, ad = c->ad, P = n.P, ROW = 2 * sd + 3, S = n.sum_out;
+    float* acts = (float*)malloc(sizeof(float) * (size_t)B * S * 2);
+    float* acts2 = acts + (size_t)B * S;
+    float* q = (float*)malloc(sizeof(float) * (size_t)B * ad * 3);
+    float* q2 = q + B * ad; float* qT = q2 + B * ad;
+    float* g = (float*)calloc((size_t)P, sizeof(float));
+    float* dbuf = (float*)calloc((size_t)S + sd, sizeof(float));
+    net_forward_batch(&n, th, rows, ROW, B, acts, q);                 /* q_values = model(states) */
+    net_forward_batch(&n, th, rows + sd + 1, ROW, B, acts2, q2);      /* next_q_values = model(next_states) */
+    net_forward_batch(&n, thT, rows + sd + 1, ROW, B, acts2, qT);     /* model_target(next_states) */
+    const float gam = (float)c->gamma, norm = (float)(2.0 / (double)B);
+    float* dq = (float*)calloc((size_t)B, sizeof(float));
+    float loss_f = 0.f, gsum = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float* r = rows + (size_t)b * ROW;
+        const int a = (int)r[sd];
+        int astar = 0;
+        for (int k = 1; k < ad; ++k) if (q2[b * ad + k] > q2[b * ad + astar]) astar = k;
+        const float y = r[2 * sd + 1] + gam * qT[b * ad + astar] * (1.f - r[2 * sd + 2]);
+        const float delta = q[b * ad + a] - y;
+        loss_f += delta * delta;
+        dq[b] = norm * delta;
+        gsum += dq[b];
+    }
+    const float loss = loss_f / (float)B;
+    const float mean_g = gsum / (float)(B * ad);   /* d/dA of -mean(A): every element gets -sum(dq)/(B*ad) */
+    for (int b = 0; b < B; ++b) {
+        const float* r = rows + (size_t)b * ROW;
+        const int a = (int)r[sd];
+        const float* A = acts + (size_t)b * S;
+        memset(dbuf, 0, sizeof(float) * (S + sd));
+        float* d = dbuf; /* gradient w.r.t. each layer output, same offsets as the activation record */
+        if (n.kind == LE_Q_DQN) {
+            const olayer* lo = &n.feat[n.nfeat - 1];
+            d[lo->y_off + a] = dq[b];
+        } else {
+            d[n.val[1].y_off] = dq[b];
+            for (int k = 0; k < ad; ++k) d[n.adv[1].y_off + k] = (k == a ? dq[b] : 0.f) - mean_g;
+            const olayer* lf = &n.feat[n.nfeat - 1];
+            layer_bwd(&n.val[1], th, g, A + n.val[0].y_off, A + n.val[1].y_off, d + n.val[1].y_off, d + n.val[0].y_off);
+            layer_bwd(&n.val[0], th, g, A + lf->y_off, A + n.val[0].y_off, d + n.val[0].y_off, d + lf->y_off);
+            layer_bwd(&n.adv[1], th, g, A + n.adv[0].y_off, A + n.adv[1].y_off, d + n.adv[1].y_off, d + n.adv[0].y_off);
+            layer_bwd(&n.adv[0], th, g, A + lf->y_off, A + n.adv[0].y_off, d + n.adv[0].y_off, d + lf->y_off);
+        }
+        for (int i = n.nfeat - 1; i >= 0; --i) {
+            const olayer* l = &n.feat[i];
+            const float* x = i > 0 ? A + n.feat[i - 1].y_off : r;
+            layer_bwd(l, th, g, x, A + l->y_off, d + l->y_off, i > 0 ? d + n.feat[i - 1].y_off : NULL);
+        }
+    }
+    *adam_t += 1;
+    const double b1d = c->beta1, b2d = c->beta2;
+    const float w1 = (float)(1.0 - b1d), b2f = (float)b2d, w2 = (float)(1.0 - b2d);
+    const double bc1 = 1.0 - pow(b1d, (double)*adam_t), bc2 = 1.0 - pow(b2d, (double)*adam_t);
+    const float neg_step = (float)(-(c->lr / bc1)), bc2s = (float)sqrt(bc2), epsf = (float)c->adam_eps;
+    const float tau = (float)c->tau, omt = (float)(1.0 - c->tau);
+    for (int p = 0; p < P; ++p) {
+        m[p] = m[p] + w1 * (g[p] - m[p]);
+        v[p] = v[p] * b2f;
+        v[p] = v[p] + w2 * g[p] * g[p];
+        const float denom = sqrtf(v[p]) / bc2s + epsf;
+        th[p] = th[p] + neg_step * m[p] / denom;
+        thT[p] = tau * th[p] + omt * thT[p];
+    }
+    free(acts); free(q); free(g); free(dbuf); free(dq);
+    return loss;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -240,6 +410,7 @@ static void real_reset(int real_env, const uint32_t w[4], double st[4]) {
 
 float le_oracle_td_update(const le_lane_cfg* c, float* th, float* thT, float* m, float* v, int32_t* adam_t,
                           const float* rows, int B) {
+    if (!is_simple_dqn(c)) return td_update_general(c, th, thT, m, v, adam_t, rows, B);
     const int sd = c->sd, ad = c->ad, H = c->q_hidden, act = c->q_act;
     const int P = le_oracle_q_params(c);
     const int ROW = 2 * sd + 3;
@@ -459,6 +630,22 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
 /* torch default nn.Linear init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias, drawn from the
  * P_QINIT stream in canonical parameter order (distribution of models/model_utils.py:31,38; the stream is ours). */
 void le_oracle_q_init(const le_lane_cfg* c, uint32_t k0, uint32_t k1, float* th) {
+    if (!is_simple_dqn(c)) {
+        onet n; build_net(c, &n);
+        const olayer* ls[8]; int nl = 0;
+        for (int i = 0; i < n.nfeat; ++i) ls[nl++] = &n.feat[i];
+        if (n.kind == LE_Q_DUELING) { ls[nl++] = &n.val[0]; ls[nl++] = &n.val[1]; ls[nl++] = &n.adv[0]; ls[nl++] = &n.adv[1]; }
+        for (int li = 0; li < nl; ++li) {
+            const double bnd = 1.0 / sqrt((double)ls[li]->in);
+            const int end = ls[li]->b_off + ls[li]->out;
+            for (int p = ls[li]->w_off; p < end; ++p) {
+                uint32_t w[4];
+                le_oracle_philox((uint32_t)(p >> 2), 0, LE_P_QINIT, 0, k0, k1, w);
+                th[p] = (float)((2.0 * (((double)w[p & 3] + 0.5) * (1.0 / 4294967296.0)) - 1.0) * bnd);
+            }
+        }
+        return;
+    }
     const int sd = c->sd, H = c->q_hidden, P = le_oracle_q_params(c);
     const int n1 = H * sd + H;
     const double bnd1 = 1.0 / sqrt((double)sd), bnd2 = 1.0 / sqrt((double)H);

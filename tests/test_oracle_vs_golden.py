@@ -40,11 +40,12 @@ def test_rn_reward_types():
             c_oracle.rn_reward(cfg, g["theta"], g["s"][0], g["s2"][0], 1.0)
 
 
-@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn"])
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2"])
 def test_td_update(tag):
     g = load_golden("td_update_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
     th = g["q_init"].copy()
+    assert th.size == cfg.q_params()
     thT = th.copy()
     m = np.zeros_like(th)
     v = np.zeros_like(th)
@@ -54,8 +55,11 @@ def test_td_update(tag):
         assert rel_err(loss, g["losses"][k]) < RTOL
         # parameters: 1e-5 relative to the parameter scale (Adam's m/sqrt(v) amplifies ulp noise of tiny gradients)
         scale = np.maximum(np.abs(g["thetas"][k]), 1e-2)
-        assert np.max(np.abs(th - g["thetas"][k]) / scale) < 5e-5
-        assert np.max(np.abs(thT - g["targets"][k]) / scale) < 5e-5
+        # Adam moves every parameter by <= lr per step whatever the gradient's magnitude, so ulp-level differences in
+        # near-zero gradients show up as a fraction of lr: tolerance 5e-5 (lr 3e-4 .. 3e-3) / 2e-4 (dueling, lr 9e-3)
+        ptol = 2e-4 if "dueling" in tag else 5e-5
+        assert np.max(np.abs(th - g["thetas"][k]) / scale) < ptol
+        assert np.max(np.abs(thT - g["targets"][k]) / scale) < ptol
     assert np.max(np.abs(m - g["adam_m"])) < 1e-5 * max(1.0, np.abs(g["adam_m"]).max())
     assert np.max(np.abs(v - g["adam_v"])) < 1e-5 * max(1.0, np.abs(g["adam_v"]).max())
 
@@ -76,7 +80,7 @@ def test_real_env_dynamics(tag, stepfn):
             assert r == np.float32(g["ep%d_rewards" % ep][t]) and bool(d) == bool(g["ep%d_dones" % ep][t])
 
 
-@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest"])
+@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling"])
 def test_trajectory_lockstep(tag):
     g = load_golden("trajectory_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
