@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import config as le_config
 from . import ops
-from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, REAL_ENV_IDS, LaneCfg
+from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, Q_DQN, Q_DUELING, REAL_ENV_IDS, LaneCfg
 from .envs import EnvFactory, EnvWrapper, _cuda_device, build_nn_from_config
 from .rng import lane_keys
 from .utils import ReplayBuffer, to_one_hot_encoding
@@ -42,20 +42,49 @@ class Critic_DQN(nn.Module):
             self.bind(flat)
 
     def bind(self, flat):
-        """Re-point every nn.Linear parameter at a slice of `flat` (torch order: W1, b1, W2, b2)."""
-        off = 0
-        for l in self.net.modules():
-            if isinstance(l, nn.Linear):
-                for name in ("weight", "bias"):
-                    p = getattr(l, name)
-                    n = p.numel()
-                    view = flat[off:off + n].view(p.shape)
-                    setattr(l, name, nn.Parameter(view, requires_grad=False))
-                    off += n
-        assert off == flat.numel()
+        """Re-point every nn.Linear parameter at a slice of `flat` (torch order: W1, b1, W2, b2, ...)."""
+        _bind_linear_params(self, flat)
 
     def forward(self, state):
         return self.net(state)
+
+
+def _bind_linear_params(module, flat):
+    """Re-point every nn.Linear parameter of `module` (in module order = state_dict order) at a slice of `flat`."""
+    off = 0
+    for l in module.modules():
+        if isinstance(l, nn.Linear):
+            for name in ("weight", "bias"):
+                p = getattr(l, name)
+                n = p.numel()
+                setattr(l, name, nn.Parameter(flat[off:off + n].view(p.shape), requires_grad=False))
+                off += n
+    assert off == flat.numel()
+
+
+class Critic_DuelingDQN(nn.Module):
+    """models/actor_critic.py:94-122: feature stream -> value head + advantage head, q = V + (A - A.mean())."""
+
+    def __init__(self, state_dim, action_dim, agent_name, config, flat=None):
+        super().__init__()
+        c = config["agents"][agent_name]
+        self.feature_stream = build_nn_from_config(input_dim=state_dim, output_dim=c["feature_dim"], nn_config=c)
+        heads = copy.copy(c)
+        heads["hidden_layer"] = 1
+        heads["hidden_size"] = c["feature_dim"]
+        self.value_stream = build_nn_from_config(input_dim=c["feature_dim"], output_dim=1, nn_config=heads)
+        self.advantage_stream = build_nn_from_config(input_dim=c["feature_dim"], output_dim=action_dim, nn_config=heads)
+        if flat is not None:
+            self.bind(flat)
+
+    def bind(self, flat):
+        _bind_linear_params(self, flat)
+
+    def forward(self, state):
+        features = self.feature_stream(state)
+        values = self.value_stream(features)
+        advantages = self.advantage_stream(features)
+        return values + (advantages - advantages.mean())
 
 
 class BaseAgent(nn.Module):
@@ -77,8 +106,12 @@ class BaseAgent(nn.Module):
 
 
 class DDQN(BaseAgent):
+    _AGENT_NAME = "ddqn"
+    _CRITIC = Critic_DQN
+    _Q_KIND = Q_DQN
+
     def __init__(self, env, config, icm=False):
-        self.agent_name = "ddqn"
+        self.agent_name = self._AGENT_NAME
         super().__init__(agent_name=self.agent_name, env=env, config=config)
         if icm:
             raise NotImplementedError("the ICM baseline branch (models/icm_baseline.py) is outside the hot path")
@@ -94,20 +127,23 @@ class DDQN(BaseAgent):
         self.eps_min = c["eps_min"]
         self.eps_decay = c["eps_decay"]
         self.hidden_size = int(c["hidden_size"])
-        if int(c.get("hidden_layer", 1)) > 1:
-            raise NotImplementedError("Q-nets with hidden_layer > 1 are outside the compiled kernel set")
+        self.hidden_layer = max(int(c.get("hidden_layer", 1)), 1)
+        self.feature_dim = int(c.get("feature_dim", 0)) if self._Q_KIND == Q_DUELING else 0
+        if self.hidden_layer > 2:
+            raise NotImplementedError("Q-nets with hidden_layer > 2 are outside the compiled kernel set")
         if int(c.get("same_action_num", 1)) != 1:
             raise NotImplementedError("same_action_num != 1 is outside the compiled kernel set")
         self._act_id = ACT_IDS[str(c["activation_fn"])]
         self._env_name = config["env_name"]
         dev = _cuda_device()
         # torch-default initialised nets (models/model_utils.py:31,38), then flattened onto the device
-        init = Critic_DQN(self.state_dim, self.action_dim, self.agent_name, config)
-        flat = torch.cat([p.detach().reshape(-1) for p in init.parameters()]).float()
+        init = self._CRITIC(self.state_dim, self.action_dim, self.agent_name, config)
+        from .envs import linear_theta
+        flat = linear_theta(init)
         self._theta = flat.to(dev).contiguous()
         self._target = self._theta.clone()
-        self.model = Critic_DQN(self.state_dim, self.action_dim, self.agent_name, config, flat=self._theta)
-        self.model_target = Critic_DQN(self.state_dim, self.action_dim, self.agent_name, config, flat=self._target)
+        self.model = self._CRITIC(self.state_dim, self.action_dim, self.agent_name, config, flat=self._theta)
+        self.model_target = self._CRITIC(self.state_dim, self.action_dim, self.agent_name, config, flat=self._target)
         self.reset_optimizer()
         self.it = 0
         self.icm = None
@@ -128,6 +164,7 @@ class DDQN(BaseAgent):
             c.env_slope[i] = sl
         c.rn_type = int(fields.get("rn_type", 0))
         c.q_hidden, c.q_act = self.hidden_size, self._act_id
+        c.q_kind, c.q_layers, c.q_feature_dim = self._Q_KIND, self.hidden_layer, self.feature_dim
         c.batch_size, c.rb_size = int(self.batch_size), int(self.rb_size)
         c.train_episodes, c.test_episodes, c.init_episodes = int(train_episodes), int(self.test_episodes), int(self.init_episodes)
         c.max_steps = int(env.max_episode_steps())
@@ -230,6 +267,7 @@ class DDQN(BaseAgent):
         c.sd, c.ad = self.state_dim, self.action_dim
         c.real_env = REAL_ENV_IDS[self._env_name]
         c.q_hidden, c.q_act = self.hidden_size, self._act_id
+        c.q_kind, c.q_layers, c.q_feature_dim = self._Q_KIND, self.hidden_layer, self.feature_dim
         c.batch_size = int(self.batch_size)
         c.gamma, c.lr, c.tau = float(self.gamma), float(self.lr), float(self.tau)
         c.beta1, c.beta2, c.adam_eps = 0.9, 0.999, 1e-8
@@ -290,27 +328,50 @@ def vary_hyperparameters(agent_cfg, rng):
     return out
 
 
+class DuelingDDQN(DDQN):
+    """agents/DuelingDDQN.py: the same algorithm on Critic_DuelingDQN (general CTA-per-lane kernel)."""
+    _AGENT_NAME = "duelingddqn"
+    _CRITIC = Critic_DuelingDQN
+    _Q_KIND = Q_DUELING
+
+
+def _varied_config(config, agent_name, vary_name, rng, vary_feature_dim=False):
+    if not config["agents"][vary_name]["vary_hp"]:
+        return config
+    config_mod = copy.deepcopy(config)
+    a = vary_hyperparameters(config_mod["agents"][agent_name], rng)
+    if vary_feature_dim:   # agents/DuelingDDQN_vary.py:24-75 also samples feature_dim log-uniformly on [fd/3, 3 fd]
+        fd = config_mod["agents"][agent_name]["feature_dim"]
+        lo, hi = math.log(int(fd / 3) - 0.49999), math.log(int(fd * 3) + 0.49999)
+        a["feature_dim"] = int(min(max(int(round(math.exp(lo + (hi - lo) * rng.random_sample()))), int(fd / 3)), int(fd * 3)))
+    # hidden_layer 0 and 1 build the same net (models/model_utils.py:34 loops hidden_layer-1 times)
+    a["hidden_layer"] = max(a["hidden_layer"], 1)
+    config_mod["agents"][agent_name] = a
+    return config_mod
+
+
 class DDQN_vary(DDQN):
     """agents/DDQN_vary.py: DDQN with sampled lr / batch_size / hidden_size / hidden_layer."""
     _rng = np.random.RandomState()
 
     def __init__(self, env, config, icm=False):
-        self.agent_name = 'ddqn'
-        if config["agents"]["ddqn_vary"]["vary_hp"]:
-            config_mod = copy.deepcopy(config)
-            config_mod["agents"]["ddqn"] = vary_hyperparameters(config_mod["agents"]["ddqn"], self._rng)
-            # hidden_layer 0 and 1 build the same net (models/model_utils.py:34 loops hidden_layer-1 times)
-            if config_mod["agents"]["ddqn"]["hidden_layer"] == 0:
-                config_mod["agents"]["ddqn"]["hidden_layer"] = 1
-        else:
-            config_mod = config
-        print("full config: ", config_mod['agents'][self.agent_name])
+        config_mod = _varied_config(config, "ddqn", "ddqn_vary", self._rng)
+        print("full config: ", config_mod['agents']["ddqn"])
         super().__init__(env=env, config=config_mod, icm=icm)
 
 
-_OUTSIDE_HOT_PATH = {"td3", "td3_icm", "td3_vary", "td3_icm_vary", "ppo", "ppo_icm", "duelingddqn", "duelingddqn_icm",
-                     "duelingddqn_vary", "duelingddqn_icm_vary", "td3_discrete_vary", "ql", "ql_cb", "sarsa", "sarsa_cb",
-                     "ddqn_icm", "ddqn_icm_vary"}
+class DuelingDDQN_vary(DuelingDDQN):
+    """agents/DuelingDDQN_vary.py."""
+    _rng = np.random.RandomState()
+
+    def __init__(self, env, config, icm=False):
+        config_mod = _varied_config(config, "duelingddqn", "duelingddqn_vary", self._rng, vary_feature_dim=True)
+        print("full config: ", config_mod['agents']["duelingddqn"])
+        super().__init__(env=env, config=config_mod, icm=icm)
+
+
+_OUTSIDE_HOT_PATH = {"td3", "td3_icm", "td3_vary", "td3_icm_vary", "ppo", "ppo_icm", "duelingddqn_icm",
+                     "duelingddqn_icm_vary", "td3_discrete_vary", "ql", "ql_cb", "sarsa", "sarsa_cb", "ddqn_icm", "ddqn_icm_vary"}
 
 
 def select_agent(config, agent_name):
@@ -322,6 +383,10 @@ def select_agent(config, agent_name):
         return DDQN(env=dummy_env, config=config)
     if agent_name == "ddqn_vary":
         return DDQN_vary(env=dummy_env, config=config)
+    if agent_name == "duelingddqn":
+        return DuelingDDQN(env=dummy_env, config=config)
+    if agent_name == "duelingddqn_vary":
+        return DuelingDDQN_vary(env=dummy_env, config=config)
     if agent_name in _OUTSIDE_HOT_PATH:
         raise NotImplementedError("RL agent %r is outside the B200 hot path (DDQN / DDQN_vary are built)" % agent_name)
     raise NotImplementedError("Unknownn RL agent")

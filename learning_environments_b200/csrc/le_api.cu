@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 
+#include "le_general_api.h"
 #include "le_instance.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -63,6 +64,11 @@ static const InstanceOps* instance_for(const le_lane_cfg* c, int max_hidden) {
     const InstanceOps* o = le_find_instance(c->sd, c->ad, units, act);
     if (!o) le_set_error("no compiled kernel set for state_dim=%d action_dim=%d q_hidden=%d act=%d", c->sd, c->ad, max_hidden, c->q_act);
     return o;
+}
+
+static bool is_register_resident(const le_lane_cfg* c) { return c->q_kind == LE_Q_DQN && c->q_layers <= 1 && c->q_hidden <= 128; }
+static int q_params_of(const le_lane_cfg* c) {
+    return is_register_resident(c) ? c->q_hidden * (c->sd + c->ad + 1) + c->ad : general_q_params(c);
 }
 
 static int check_env_cfg(const le_lane_cfg* c) {
@@ -218,6 +224,8 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 }
 
 struct Plan {
+    bool general;
+    GeneralPlan gp;
     const InstanceOps* ops;
     int grid, slots, ring_cap;
     int64_t ring_stride_f, pack_stride_f, pack_bytes, rings_bytes, total_bytes, off_rings, off_counter;
@@ -230,22 +238,33 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
                      c->batch_size, c->rb_size, c->train_episodes, c->test_episodes, c->max_steps, n_lanes);
         return LE_EINVAL;
     }
-    const InstanceOps* ops = instance_for(c, c->q_hidden);
-    if (!ops) return LE_EUNSUPPORTED;
+    pl->general = !is_register_resident(c);
+    // the env-packing / unit kernels of any kernel set with the right (sd, ad) serve the general path too
+    const InstanceOps* ops = pl->general ? le_find_instance(c->sd, c->ad, 1, QACT_TANH) : instance_for(c, c->q_hidden);
+    if (!ops) { if (pl->general) le_set_error("no compiled kernel set for state_dim=%d action_dim=%d", c->sd, c->ad); return LE_EUNSUPPORTED; }
+    if (pl->general && qact_of(c) < 0) { le_set_error("Q-net activation id %d is outside the compiled kernel set", c->q_act); return LE_EUNSUPPORTED; }
     int dev = 0, sms = 0;
     LE_CUDA_CHECK(cudaGetDevice(&dev));
     LE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int per_sm = ops->inner_max_ctas_per_sm();
-    if (per_sm < 1) per_sm = 1;
-    const int want = (n_lanes + kWarpsPerCta - 1) / kWarpsPerCta;
-    pl->ops = ops;
-    pl->grid = want < sms * per_sm ? want : sms * per_sm;
-    pl->slots = pl->grid * kWarpsPerCta;
     int64_t max_total = (int64_t)c->train_episodes * c->max_steps;
     if (c->step_budget > 0 && c->step_budget + c->max_steps < max_total) max_total = c->step_budget + c->max_steps;
     if (max_total < 1) max_total = 1;
     pl->ring_cap = (int)((int64_t)c->rb_size < max_total ? c->rb_size : max_total);
-    pl->ring_stride_f = (int64_t)pl->ring_cap * ops->ring_row_floats();
+    pl->ops = ops;
+    if (pl->general) {
+        const int rc = general_plan(c, n_lanes, pl->ring_cap, sms, &pl->gp);
+        if (rc != LE_OK) return rc;
+        pl->grid = pl->gp.grid;
+        pl->slots = pl->grid;
+        pl->ring_stride_f = pl->gp.slot_floats;   // one slot = ring + parameters + activations
+    } else {
+        int per_sm = ops->inner_max_ctas_per_sm();
+        if (per_sm < 1) per_sm = 1;
+        const int want = (n_lanes + kWarpsPerCta - 1) / kWarpsPerCta;
+        pl->grid = want < sms * per_sm ? want : sms * per_sm;
+        pl->slots = pl->grid * kWarpsPerCta;
+        pl->ring_stride_f = (int64_t)pl->ring_cap * ops->ring_row_floats();
+    }
     const int64_t pv4 = c->env_kind == LE_ENV_SE ? ops->se_pack_vec4(c->env_hidden) : (c->env_kind == LE_ENV_RN ? ops->rn_pack_vec4(c->env_hidden) : 1);
     pl->pack_stride_f = pv4 * 4;
     pl->pack_bytes = ((int64_t)(n_env > 0 ? n_env : 1) * pl->pack_stride_f * 4 + 255) / 256 * 256;
@@ -355,6 +374,10 @@ int le_rn_reward(const le_lane_cfg* cfg, const float* theta_dev, int pop, int la
 int le_qnet_forward(const le_lane_cfg* cfg, const float* q_theta_dev, int n, const float* state_dev, float* q_out_dev,
                     int32_t* argmax_dev, void* stream) {
     if (!cfg || n < 1) { le_set_error("le_qnet_forward: bad arguments"); return LE_EINVAL; }
+    if (!is_register_resident(cfg)) {
+        if (qact_of(cfg) < 0 || !le_find_instance(cfg->sd, cfg->ad, 1, QACT_TANH)) { le_set_error("le_qnet_forward: unsupported Q-network"); return LE_EUNSUPPORTED; }
+        return general_qnet_forward(cfg, q_theta_dev, n, state_dev, q_out_dev, argmax_dev, (cudaStream_t)stream);
+    }
     const InstanceOps* ops = instance_for(cfg, cfg->q_hidden);
     if (!ops) return LE_EUNSUPPORTED;
     const int Pq = cfg->q_hidden * (cfg->sd + cfg->ad + 1) + cfg->ad;
@@ -375,12 +398,18 @@ int le_real_env_step(int real_env, int max_steps, double* state_dev, int32_t* el
 int le_td_update(const le_lane_cfg* cfg, float* q_theta_dev, float* q_target_dev, float* adam_m_dev, float* adam_v_dev,
                  int32_t* adam_t_dev, int n, const float* batch_rows_dev, float* loss_dev, void* stream) {
     if (!cfg || n < 1 || cfg->batch_size < 1) { le_set_error("le_td_update: bad arguments"); return LE_EINVAL; }
-    const InstanceOps* ops = instance_for(cfg, cfg->q_hidden);
-    if (!ops) return LE_EUNSUPPORTED;
+    const bool general = !is_register_resident(cfg);
+    const InstanceOps* ops = general ? le_find_instance(cfg->sd, cfg->ad, 1, QACT_TANH) : instance_for(cfg, cfg->q_hidden);
+    if (!ops || qact_of(cfg) < 0) { if (general) le_set_error("le_td_update: unsupported Q-network"); return LE_EUNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     le_lane_cfg* cfg_dev = nullptr;
     LE_CUDA_CHECK(cudaMallocAsync((void**)&cfg_dev, sizeof(le_lane_cfg), st));
     LE_CUDA_CHECK(cudaMemcpyAsync(cfg_dev, cfg, sizeof(le_lane_cfg), cudaMemcpyHostToDevice, st));
+    if (general) {
+        const int rc = general_td_update(cfg, cfg_dev, q_theta_dev, q_target_dev, adam_m_dev, adam_v_dev, adam_t_dev, n, batch_rows_dev, loss_dev, st);
+        cudaFreeAsync(cfg_dev, st);
+        return rc;
+    }
     const int Pq = cfg->q_hidden * (cfg->sd + cfg->ad + 1) + cfg->ad;
     LE_CUDA_CHECK(ops->launch_td_update(cfg_dev, q_theta_dev, q_target_dev, adam_m_dev, adam_v_dev, adam_t_dev, Pq, batch_rows_dev,
                                         cfg->batch_size, loss_dev, n, st));
@@ -436,14 +465,15 @@ int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* 
     P.env_pack = (const float4*)pack; P.env_pack_stride = pl.pack_stride_f / 4;
     P.env_index = env_index_dev; P.keys = keys_dev;
     P.q_init = q_init_dev; P.q_final = q_final_dev;
-    P.q_stride = c->q_hidden * (c->sd + c->ad + 1) + c->ad;
+    P.q_stride = q_params_of(c);
     P.n_lanes = n_lanes; P.out = out_dev; P.rewards = rewards_dev; P.lengths = lengths_dev; P.test_rewards = test_rewards_dev; P.test_lengths = test_lengths_dev;
     P.rew_stride = c->train_episodes > 0 ? c->train_episodes : 1;
     P.test_stride = c->test_episodes;
     P.rings = (float*)(ws + pl.off_rings); P.ring_stride = pl.ring_stride_f; P.ring_cap = pl.ring_cap;
     P.work_counter = counter;
     if (trace_host && trace_host->cap > 0) { P.trace = *trace_host; P.trace_lane = trace_lane; }
-    LE_CUDA_CHECK(pl.ops->launch_inner(P, pl.grid, st));
+    if (pl.general) LE_CUDA_CHECK(general_launch(c, P, P.rings, pl.gp, st));
+    else LE_CUDA_CHECK(pl.ops->launch_inner(P, pl.grid, st));
     return LE_OK;
 }
 
@@ -472,7 +502,7 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
     Plan pl;
     int rc = make_plan(c, n_lanes, n_env, &pl);
     if (rc != LE_OK) return rc;
-    const int Pq = c->q_hidden * (c->sd + c->ad + 1) + c->ad;
+    const int Pq = q_params_of(c);
     const int P_env = c->env_kind == LE_ENV_SE ? 3 * c->env_hidden * (c->sd + c->ad + 1) + c->env_hidden * (c->sd + 2) + c->sd + 2
                                               : (c->env_kind == LE_ENV_RN ? c->env_hidden * (c->sd + 2) + 1 : 0);
     const int rs = c->train_episodes > 0 ? c->train_episodes : 1;

@@ -1,0 +1,637 @@
+// le_general.cuh — CTA-per-lane kernels for Q-networks that do not fit one warp's registers:
+//   Critic_DuelingDQN (models/actor_critic.py:94-122, 11.5k .. 67k parameters), Critic_DQN with two hidden layers or
+//   more than 128 hidden units (DDQN_vary tails, agents/DDQN_vary.py:26-59).
+// One CTA (256 threads) owns one lane; parameters, Adam state, gradients and the minibatch activations live in the
+// lane slot's HBM workspace (L2-resident: <= 2.5 MB per slot) and every dense layer is a 64x64x16 shared-memory-tiled
+// FFMA GEMM with a 4x4 register tile per thread (forward NT, input-gradient NN, weight-gradient TN through one
+// strided routine).  The control flow (episodes, eps-greedy, env step, replay ring, tests, early-out) mirrors
+// le_inner_loop.cuh; scalars are computed redundantly by all threads (uniform), warp 0 runs the SE/RN mat-vec.
+//
+// Dueling coupling (models/actor_critic.py:121): q = V + (A - A.mean()) with the mean over the WHOLE batch tensor, so
+// the forward needs a CTA-wide reduction before the TD error and the backward seeds dA = dq*[a=a_r] - sum(dq)/(B*AD).
+#pragma once
+#include "le_inner_loop.cuh"
+
+namespace le {
+
+constexpr int kGThreads = 256;
+constexpr int kGTile = 64, kGChunk = 16, kGPad = 4;
+
+struct GLayer { int in, out, act, w_off, b_off, y_off; };
+struct GNet {
+    int kind, nfeat, P, sum_out, sd, ad;
+    float slope;
+    GLayer feat[4], val[2], adv[2];
+};
+
+inline void gnet_add(GLayer* l, int in, int out, int act, int* p, int* y) {
+    l->in = in; l->out = out; l->act = act; l->w_off = *p; *p += in * out; l->b_off = *p; *p += out; l->y_off = *y; *y += out;
+}
+// same construction as oracle/le_oracle.c build_net (torch state_dict order)
+inline void gnet_build(const le_lane_cfg* c, GNet* n) {
+    int p = 0, y = 0;
+    const int L = c->q_layers > 1 ? c->q_layers : 1, H = c->q_hidden;
+    const int act = c->q_act == LE_ACT_TANH ? 1 : 2;
+    n->kind = c->q_kind; n->sd = c->sd; n->ad = c->ad; n->nfeat = 0;
+    n->slope = c->q_act == LE_ACT_LEAKYRELU ? 0.01f : 0.f;
+    gnet_add(&n->feat[n->nfeat++], c->sd, H, act, &p, &y);
+    for (int i = 1; i < L; ++i) gnet_add(&n->feat[n->nfeat++], H, H, act, &p, &y);
+    if (c->q_kind == LE_Q_DQN) {
+        gnet_add(&n->feat[n->nfeat++], H, c->ad, 0, &p, &y);
+    } else {
+        const int fd = c->q_feature_dim;
+        gnet_add(&n->feat[n->nfeat++], H, fd, 0, &p, &y);
+        gnet_add(&n->val[0], fd, fd, act, &p, &y);
+        gnet_add(&n->val[1], fd, 1, 0, &p, &y);
+        gnet_add(&n->adv[0], fd, fd, act, &p, &y);
+        gnet_add(&n->adv[1], fd, c->ad, 0, &p, &y);
+    }
+    n->P = p; n->sum_out = y;
+}
+
+__device__ __forceinline__ float g_act(int act, float slope, float z) {
+    if (act == 1) return tanh_one(z);
+    if (act == 2) return fmaxf(z, slope * z);
+    return z;
+}
+__device__ __forceinline__ float g_act_grad(int act, float slope, float h) {
+    if (act == 1) return fmaf(-h, h, 1.f);
+    if (act == 2) return h > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+// C[i*c_si + j*c_sj] (+)= sum_l A[i*a_si + l*a_sl] * B[l*b_sl + j*b_sj]  (+ bias[j], activation)   — whole CTA.
+__device__ void g_gemm(const float* __restrict__ A, int a_si, int a_sl, const float* __restrict__ B, int b_sl, int b_sj,
+                       float* __restrict__ C, int c_si, int c_sj, int I, int J, int L, const float* __restrict__ bias, int act,
+                       float slope, bool accumulate, float* sm) {
+    float* As = sm;
+    float* Bs = sm + kGChunk * (kGTile + kGPad);
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    constexpr int LD = kGTile + kGPad;
+    for (int i0 = 0; i0 < I; i0 += kGTile) {
+        for (int j0 = 0; j0 < J; j0 += kGTile) {
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            for (int l0 = 0; l0 < L; l0 += kGChunk) {
+#pragma unroll
+                for (int q = 0; q < (kGTile * kGChunk) / kGThreads; ++q) {
+                    const int e = tid + kGThreads * q;
+                    int l, i;
+                    if (a_sl == 1) { l = e & (kGChunk - 1); i = e >> 4; } else { i = e & (kGTile - 1); l = e >> 6; }
+                    const int gi = i0 + i, gl = l0 + l;
+                    As[l * LD + i] = (gi < I && gl < L) ? A[(int64_t)gi * a_si + (int64_t)gl * a_sl] : 0.f;
+                    int lb, j;
+                    if (b_sl == 1) { lb = e & (kGChunk - 1); j = e >> 4; } else { j = e & (kGTile - 1); lb = e >> 6; }
+                    const int gj = j0 + j, glb = l0 + lb;
+                    Bs[lb * LD + j] = (gj < J && glb < L) ? B[(int64_t)glb * b_sl + (int64_t)gj * b_sj] : 0.f;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int l = 0; l < kGChunk; ++l) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(As + l * LD + 4 * ty);
+                    const float4 b4 = *reinterpret_cast<const float4*>(Bs + l * LD + 4 * tx);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = i0 + 4 * ty + a;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int j = j0 + 4 * tx + b;
+                    if (i < I && j < J) {
+                        float v = acc[a][b];
+                        float* dst = C + (int64_t)i * c_si + (int64_t)j * c_sj;
+                        if (accumulate) v += *dst;
+                        if (bias) v += bias[j];
+                        *dst = g_act(act, slope, v);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void g_layer_fwd(const GLayer& l, const float* th, const float* X, int xs, int B, float* acts, int S,
+                                            float slope, float* sm) {
+    g_gemm(X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, sm);
+}
+
+// all layers for B rows; returns nothing: activations are in `acts` (row stride S = net.sum_out)
+__device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm) {
+    const int S = n.sum_out;
+    const float* in = X;
+    int in_s = xs;
+    for (int i = 0; i < n.nfeat; ++i) {
+        g_layer_fwd(n.feat[i], th, in, in_s, B, acts, S, n.slope, sm);
+        in = acts + n.feat[i].y_off;
+        in_s = S;
+    }
+    if (n.kind == LE_Q_DUELING) {
+        g_layer_fwd(n.val[0], th, in, S, B, acts, S, n.slope, sm);
+        g_layer_fwd(n.val[1], th, acts + n.val[0].y_off, S, B, acts, S, n.slope, sm);
+        g_layer_fwd(n.adv[0], th, in, S, B, acts, S, n.slope, sm);
+        g_layer_fwd(n.adv[1], th, acts + n.adv[0].y_off, S, B, acts, S, n.slope, sm);
+    }
+}
+
+// CTA-wide sum of one float per thread; result broadcast to all threads. red: >= 32 floats of shared memory.
+__device__ __forceinline__ float g_block_sum(float v, float* red) {
+    v = warp_allreduce_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+// q[b][a] for B rows from the activation record: DQN -> output layer; dueling -> V + (A - mean(A over batch x actions))
+__device__ void g_q_values(const GNet& n, const float* acts, int B, float* q, float* red) {
+    const int S = n.sum_out, AD = n.ad;
+    if (n.kind == LE_Q_DQN) {
+        const int yo = n.feat[n.nfeat - 1].y_off;
+        for (int e = threadIdx.x; e < B * AD; e += kGThreads) q[e] = acts[(int64_t)(e / AD) * S + yo + (e % AD)];
+        __syncthreads();
+        return;
+    }
+    const int ao = n.adv[1].y_off, vo = n.val[1].y_off;
+    float part = 0.f;
+    for (int e = threadIdx.x; e < B * AD; e += kGThreads) part += acts[(int64_t)(e / AD) * S + ao + (e % AD)];
+    const float mean = g_block_sum(part, red) / (float)(B * AD);
+    for (int e = threadIdx.x; e < B * AD; e += kGThreads) {
+        const int b = e / AD, a = e % AD;
+        q[e] = acts[(int64_t)b * S + vo] + (acts[(int64_t)b * S + ao + a] - mean);
+    }
+    __syncthreads();
+}
+
+// backward of one dense layer for B rows. dact holds dL/dY at l.y_off (overwritten by dZ); X/xs: the layer's input.
+// dX (may be null) receives / accumulates dL/dX with row stride dxs.
+__device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const float* X, int xs, const float* acts, float* dact,
+                            int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm) {
+    for (int e = threadIdx.x; e < B * l.out; e += kGThreads) {
+        const int64_t o = (int64_t)(e / l.out) * S + l.y_off + (e % l.out);
+        dact[o] *= g_act_grad(l.act, slope, acts[o]);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < l.out; o += kGThreads) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += dact[(int64_t)b * S + l.y_off + o];
+        grad[l.b_off + o] = s;
+    }
+    // dW[o][i] = sum_b dZ[b][o] * X[b][i]
+    g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
+    // dX[b][i] (+)= sum_o dZ[b][o] * W[o][i]
+    if (dX) g_gemm(dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, sm);
+}
+
+// Device-side view of one lane slot's workspace
+struct GSlot {
+    float *ring, *theta, *thetaT, *m, *v, *grad, *xs, *xs2, *misc, *actA, *actB, *dact, *q, *q2, *qT, *dq, *obs;
+    int* astar;
+};
+
+// DDQN.learn / DuelingDDQN.learn on the B rows staged in slot.xs / xs2 / misc (misc = [a, r, d, pad] per row)
+__device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red) {
+    const int S = n.sum_out, AD = n.ad, SDs = n.sd;
+    g_net_forward(n, w.theta, w.xs, SDs, B, w.actA, sm);    // q_values = model(states)            (activations kept)
+    g_q_values(n, w.actA, B, w.q, red);
+    g_net_forward(n, w.theta, w.xs2, SDs, B, w.actB, sm);   // next_q_values = model(next_states)
+    g_q_values(n, w.actB, B, w.q2, red);
+    g_net_forward(n, w.thetaT, w.xs2, SDs, B, w.actB, sm);  // model_target(next_states)
+    g_q_values(n, w.actB, B, w.qT, red);
+    float lpart = 0.f, gpart = 0.f;
+    for (int b = threadIdx.x; b < B; b += kGThreads) {
+        const int a = (int)w.misc[4 * b];
+        int astar = 0;
+        float best = w.q2[b * AD];
+        for (int k = 1; k < AD; ++k)
+            if (w.q2[b * AD + k] > best) { best = w.q2[b * AD + k]; astar = k; }
+        const float y = w.misc[4 * b + 1] + (ls.gamma * w.qT[b * AD + astar]) * (1.f - w.misc[4 * b + 2]);
+        const float delta = w.q[b * AD + a] - y;
+        lpart = fmaf(delta, delta, lpart);
+        const float dq = ls.norm * delta;
+        w.dq[b] = dq;
+        gpart += dq;
+    }
+    const float loss = g_block_sum(lpart, red) / (float)B;
+    const float mean_g = g_block_sum(gpart, red) / (float)(B * AD);
+    // seed dL/d(outputs)
+    if (n.kind == LE_Q_DQN) {
+        const int yo = n.feat[n.nfeat - 1].y_off;
+        for (int e = threadIdx.x; e < B * AD; e += kGThreads) {
+            const int b = e / AD, k = e % AD;
+            w.dact[(int64_t)b * S + yo + k] = ((int)w.misc[4 * b] == k) ? w.dq[b] : 0.f;
+        }
+    } else {
+        const int ao = n.adv[1].y_off, vo = n.val[1].y_off;
+        for (int e = threadIdx.x; e < B * AD; e += kGThreads) {
+            const int b = e / AD, k = e % AD;
+            w.dact[(int64_t)b * S + ao + k] = (((int)w.misc[4 * b] == k) ? w.dq[b] : 0.f) - mean_g;
+            if (k == 0) w.dact[(int64_t)b * S + vo] = w.dq[b];
+        }
+    }
+    __syncthreads();
+    const GLayer& lf = n.feat[n.nfeat - 1];
+    if (n.kind == LE_Q_DUELING) {
+        g_layer_bwd(n.val[1], w.theta, w.grad, w.actA + n.val[0].y_off, S, w.actA, w.dact, S, B, w.dact + n.val[0].y_off, S, false, n.slope, sm);
+        g_layer_bwd(n.val[0], w.theta, w.grad, w.actA + lf.y_off, S, w.actA, w.dact, S, B, w.dact + lf.y_off, S, false, n.slope, sm);
+        g_layer_bwd(n.adv[1], w.theta, w.grad, w.actA + n.adv[0].y_off, S, w.actA, w.dact, S, B, w.dact + n.adv[0].y_off, S, false, n.slope, sm);
+        g_layer_bwd(n.adv[0], w.theta, w.grad, w.actA + lf.y_off, S, w.actA, w.dact, S, B, w.dact + lf.y_off, S, true, n.slope, sm);
+    }
+    for (int i = n.nfeat - 1; i >= 0; --i) {
+        const GLayer& l = n.feat[i];
+        const float* X = i > 0 ? w.actA + n.feat[i - 1].y_off : w.xs;
+        const int xs = i > 0 ? S : SDs;
+        g_layer_bwd(l, w.theta, w.grad, X, xs, w.actA, w.dact, S, B, i > 0 ? w.dact + n.feat[i - 1].y_off : nullptr, S, false, n.slope, sm);
+    }
+    // Adam + Polyak (same operation order as LaneCore::adam_one)
+    ls.b1pow *= ls.beta1;
+    ls.b2pow *= ls.beta2d;
+    const double bc1 = 1.0 - ls.b1pow, bc2 = 1.0 - ls.b2pow;
+    const float neg_step = (float)(-(ls.lr / bc1));
+    const float bc2s = (float)sqrt(bc2);
+    for (int p = threadIdx.x; p < n.P; p += kGThreads) {
+        const float g = w.grad[p];
+        float m = w.m[p], v = w.v[p];
+        m = m + ls.w1 * (g - m);
+        v = v * ls.beta2;
+        v = v + (ls.w2 * g) * g;
+        w.m[p] = m;
+        w.v[p] = v;
+        const float denom = __fdiv_rn(__fsqrt_rn(v), bc2s) + ls.eps;
+        const float pn = w.theta[p] + __fdiv_rn(neg_step * m, denom);
+        w.theta[p] = pn;
+        w.thetaT[p] = ls.tau * pn + ls.one_minus_tau * w.thetaT[p];
+    }
+    __syncthreads();
+    return loss;
+}
+
+// greedy action of ONE state row (select_train/test_action); result uniform across the CTA
+__device__ int g_greedy_row(const GNet& n, const GSlot& w, const float* state_sm /* [sd] in shared memory */, float* sm, float* red,
+                            int* ibox) {
+    g_net_forward(n, w.theta, state_sm, n.sd, 1, w.actB, sm);
+    g_q_values(n, w.actB, 1, w.q2, red);
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int k = 1; k < n.ad; ++k)
+            if (w.q2[k] > w.q2[best]) best = k;
+        *ibox = best;
+    }
+    __syncthreads();
+    const int a = *ibox;
+    __syncthreads();
+    return a;
+}
+
+struct GRunParams {
+    RunParams rp;            // same lane-level inputs/outputs as the warp kernel
+    GNet net;
+    float* slots; int64_t slot_stride;   // floats per CTA slot
+    int bmax;
+};
+
+__host__ __device__ inline int64_t gslot_floats(const GNet& n, int ring_cap, int rowf, int bmax, int64_t* offs /* [18] */) {
+    const int Pp = (n.P + 3) / 4 * 4;
+    const int64_t BS = (int64_t)bmax * n.sum_out;
+    int64_t o = 0;
+    int k = 0;
+    auto take = [&](int64_t nfl) { offs[k++] = o; o += (nfl + 3) / 4 * 4; };
+    take((int64_t)ring_cap * rowf);          // 0 ring
+    take(Pp); take(Pp); take(Pp); take(Pp); take(Pp);   // 1..5 theta thetaT m v grad
+    take((int64_t)bmax * n.sd); take((int64_t)bmax * n.sd); take((int64_t)bmax * 4);   // 6 xs, 7 xs2, 8 misc
+    take(BS); take(BS); take(BS);            // 9 actA, 10 actB, 11 dact
+    take((int64_t)bmax * n.ad); take((int64_t)bmax * n.ad); take((int64_t)bmax * n.ad);   // 12 q, 13 q2, 14 qT
+    take(bmax); take((int64_t)64 * n.sd); take(bmax);   // 15 dq, 16 obs, 17 astar
+    return o;
+}
+
+__device__ inline GSlot gslot_view(float* base, const GNet& n, int ring_cap, int rowf, int bmax) {
+    int64_t offs[18];
+    gslot_floats(n, ring_cap, rowf, bmax, offs);
+    GSlot s;
+    s.ring = base + offs[0]; s.theta = base + offs[1]; s.thetaT = base + offs[2]; s.m = base + offs[3]; s.v = base + offs[4];
+    s.grad = base + offs[5]; s.xs = base + offs[6]; s.xs2 = base + offs[7]; s.misc = base + offs[8]; s.actA = base + offs[9];
+    s.actB = base + offs[10]; s.dact = base + offs[11]; s.q = base + offs[12]; s.q2 = base + offs[13]; s.qT = base + offs[14];
+    s.dq = base + offs[15]; s.obs = base + offs[16]; s.astar = reinterpret_cast<int*>(base + offs[17]);
+    return s;
+}
+
+// torch default nn.Linear init of a general net from the P_QINIT stream (same stream as the CPU restatement)
+__device__ void g_init_layer(const GLayer& l, float* th, uint32_t k0, uint32_t k1) {
+    const double bnd = 1.0 / sqrt((double)l.in);
+    const int end = l.b_off + l.out;
+    for (int p = l.w_off + threadIdx.x; p < end; p += kGThreads) {
+        const u32x4 w = philox4x32_10((uint32_t)(p >> 2), 0u, LE_P_QINIT, 0u, k0, k1);
+        th[p] = (float)((2.0 * (((double)pick(w, p & 3) + 0.5) * (1.0 / 4294967296.0)) - 1.0) * bnd);
+    }
+}
+
+template <int SD, int AD>
+__global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParams G) {
+    using RL = RowLayout<SD>;
+    __shared__ __align__(16) float sm[2 * kGChunk * (kGTile + kGPad)];
+    __shared__ float red[32];
+    __shared__ __align__(16) float box[16];   // state row / env step results broadcast
+    __shared__ int ibox[4];
+    __shared__ double dred[kGThreads / 32];
+    __shared__ int sred[kGThreads / 32];
+    __shared__ le_lane_cfg cfg_sm;
+    const RunParams& P = G.rp;
+    const GNet& n = G.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const GSlot w = gslot_view(G.slots + (int64_t)blockIdx.x * G.slot_stride, n, P.ring_cap, RL::ROWF, G.bmax);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) ibox[0] = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int lane_id = ibox[0];
+        if (lane_id >= P.n_lanes) break;
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(P.cfg + (P.n_cfg == 1 ? 0 : lane_id));
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&cfg_sm);
+            for (int i = tid; i < (int)(sizeof(le_lane_cfg) / 4); i += kGThreads) dst[i] = src[i];
+        }
+        __syncthreads();
+        const le_lane_cfg& c = cfg_sm;
+        const uint32_t k0 = P.keys[2 * lane_id], k1 = P.keys[2 * lane_id + 1];
+        const float4* pack = P.env_pack + (int64_t)(P.env_index ? P.env_index[lane_id] : 0) * P.env_pack_stride;
+        const bool env_tanh = c.env_act == LE_ACT_TANH;
+        double* rewards = P.rewards + (int64_t)lane_id * P.rew_stride;
+        int32_t* lengths = P.lengths + (int64_t)lane_id * P.rew_stride;
+        double* test_rewards = P.test_rewards + (int64_t)lane_id * P.test_stride;
+        const bool tracing = P.trace.cap > 0 && lane_id == P.trace_lane;
+        // ---- agent construction
+        if (P.q_init) { for (int p = tid; p < n.P; p += kGThreads) w.theta[p] = P.q_init[(int64_t)lane_id * P.q_stride + p]; }
+        else {
+            for (int i = 0; i < n.nfeat; ++i) g_init_layer(n.feat[i], w.theta, k0, k1);
+            if (n.kind == LE_Q_DUELING) { g_init_layer(n.val[0], w.theta, k0, k1); g_init_layer(n.val[1], w.theta, k0, k1);
+                                          g_init_layer(n.adv[0], w.theta, k0, k1); g_init_layer(n.adv[1], w.theta, k0, k1); }
+        }
+        __syncthreads();
+        for (int p = tid; p < n.P; p += kGThreads) { w.thetaT[p] = w.theta[p]; w.m[p] = 0.f; w.v[p] = 0.f; }
+        __syncthreads();
+        LearnScalars ls;
+        fill_learn_scalars(ls, c);
+
+        // greedy test rollouts on the real env, episodes = rows of one batched forward per step
+        auto run_test = [&](int test_call, double* ep_out, int32_t* len_out, int64_t& test_steps) -> double {
+            double total = 0.0;
+            for (int ep0 = 0; ep0 < c.test_episodes; ep0 += 64) {
+                const int M = min(64, c.test_episodes - ep0);
+                double st[4] = {0, 0, 0, 0};
+                float obs[SD];
+                int elapsed = 0, ep_steps = 0;
+                float ep_rew = 0.f;
+                bool running = tid < M;
+                if (tid < M) {
+                    real_reset(c.real_env, philox4x32_10((uint32_t)test_call, (uint32_t)(ep0 + tid), LE_P_RESET_TEST, 0u, k0, k1), st);
+                    real_obs<SD>(c.real_env, st, obs);
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) w.obs[tid * SD + i] = obs[i];
+                }
+                for (int t = 0; t < c.max_steps; ++t) {
+                    if (!__syncthreads_or(running ? 1 : 0)) break;
+                    g_net_forward(n, w.theta, w.obs, SD, M, w.actB, sm);
+                    g_q_values(n, w.actB, M, w.q2, red);
+                    if (running) {
+                        int best = 0;
+                        for (int k = 1; k < AD; ++k)
+                            if (w.q2[tid * AD + k] > w.q2[tid * AD + best]) best = k;
+                        float r, d;
+                        real_step<SD>(c.real_env, c.max_steps, st, elapsed, best, obs, r, d);
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) w.obs[tid * SD + i] = obs[i];
+                        ep_rew += r;
+                        ep_steps += 1;
+                        if (d > 0.5f) running = false;
+                    }
+                }
+                __syncthreads();
+                float rsum = (tid < M) ? ep_rew : 0.f;
+                if (tid < M) {
+                    if (ep_out) ep_out[ep0 + tid] = (double)ep_rew;
+                    if (len_out) len_out[ep0 + tid] = ep_steps;
+                }
+                // episode rewards are small integers / short fp32 sums: an fp32 CTA sum would round; sum in double via shared memory
+                double dv = (double)rsum;
+                dv = warp_allreduce_sum(dv);
+                int sv = (tid < M) ? ep_steps : 0;
+#pragma unroll
+                for (int mm = 16; mm > 0; mm >>= 1) sv += __shfl_xor_sync(LE_FULL_MASK, sv, mm);
+                __syncthreads();
+                if (lane == 0) { dred[warp] = dv; sred[warp] = sv; }
+                __syncthreads();
+                for (int q = 0; q < kGThreads / 32; ++q) { total += dred[q]; test_steps += sred[q]; }
+                __syncthreads();
+            }
+            return total / (double)c.test_episodes;
+        };
+
+        int rb_ptr = 0, rb_size = 0;
+        int64_t train_steps = 0, learn_iters = 0, test_steps = 0;
+        int test_calls = 0, n_ep = 0, timed_out = 0;
+        double eps = c.eps_init;
+        const bool rule_virtual = (!c.use_test_env) && c.env_kind == LE_ENV_SE;
+        for (int episode = 0; episode < c.train_episodes; ++episode) {
+            if (c.step_budget > 0 && train_steps >= c.step_budget) { timed_out = 1; break; }
+            if (episode == 0) eps = c.eps_init;
+            else { eps *= c.eps_decay; if (eps < c.eps_min) eps = c.eps_min; }
+            double st[4];
+            real_reset(c.real_env, philox4x32_10((uint32_t)episode, 0u, LE_P_RESET_TRAIN, 0u, k0, k1), st);
+            float state[SD];
+            real_obs<SD>(c.real_env, st, state);
+            int elapsed = 0, ep_len = 0;
+            float ep_rew = 0.f;
+            for (int t = 0; t < c.max_steps; ++t) {
+                const u32x4 wa = philox4x32_10((uint32_t)train_steps, 0u, LE_P_ACT, 0u, k0, k1);
+                const bool explore = ((double)(wa.x >> 8) * (1.0 / 16777216.0)) < eps;
+                int action;
+                if (explore) action = (int)__umulhi(wa.y, (uint32_t)AD);
+                else {
+                    __syncthreads();
+                    if (tid < SD) box[tid] = state[tid];
+                    __syncthreads();
+                    action = g_greedy_row(n, w, box, sm, red, ibox);
+                }
+                float ns[SD], r, d;
+                if (c.env_kind == LE_ENV_SE) {
+                    __syncthreads();
+                    if (warp == 0) {
+                        float ns0[SD], r0, d0;
+                        se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, state, action, lane, ns0, r0, d0);
+                        if (lane == 0) {
+#pragma unroll
+                            for (int i = 0; i < SD; ++i) box[i] = ns0[i];
+                            box[SD] = r0; box[SD + 1] = d0;
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) ns[i] = box[i];
+                    r = box[SD]; d = box[SD + 1];
+                    __syncthreads();
+                } else {
+                    float rr;
+                    real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
+                    if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
+                        __syncthreads();
+                        if (warp == 0) {
+                            float ps, ps2;
+                            rn_phi2<SD>(pack, c.env_hidden, env_tanh, state, ns, lane, ps, ps2);
+                            if (lane == 0) box[0] = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
+                        }
+                        __syncthreads();
+                        r = box[0];
+                        __syncthreads();
+                    } else r = rr;
+                }
+                {   // replay_buffer.add
+                    float rowv[RL::ROWF];
+#pragma unroll
+                    for (int i = 0; i < RL::ROWF; ++i) rowv[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) { rowv[RL::OFF_S + i] = state[i]; rowv[RL::OFF_S2 + i] = ns[i]; }
+                    rowv[RL::OFF_A] = (float)action; rowv[RL::OFF_R] = r; rowv[RL::OFF_D] = d;
+                    float4* dst = reinterpret_cast<float4*>(w.ring + (int64_t)rb_ptr * RL::ROWF);
+#pragma unroll
+                    for (int q = 0; q < RL::ROW_VEC; ++q)
+                        if (tid == q) __stcg(dst + q, make_float4(rowv[4 * q], rowv[4 * q + 1], rowv[4 * q + 2], rowv[4 * q + 3]));
+                    rb_ptr = (rb_ptr + 1 == P.ring_cap) ? 0 : rb_ptr + 1;
+                    rb_size = rb_size + 1 < P.ring_cap ? rb_size + 1 : P.ring_cap;
+                }
+#pragma unroll
+                for (int i = 0; i < SD; ++i) state[i] = ns[i];
+                ep_rew += r;
+                ep_len += 1;
+                float loss = __int_as_float(0x7fc00000);
+                if (episode >= c.init_episodes) {
+                    __syncthreads();
+                    const int B = ls.batch;
+                    for (int b = tid; b < B; b += kGThreads) {   // replay_buffer.sample on the P_SAMPLE stream
+                        const u32x4 wv = philox4x32_10((uint32_t)learn_iters, (uint32_t)(b >> 2), LE_P_SAMPLE, 0u, k0, k1);
+                        const uint32_t idx = __umulhi(pick(wv, b & 3), (uint32_t)rb_size);
+                        const float4* src = reinterpret_cast<const float4*>(w.ring + (int64_t)idx * RL::ROWF);
+                        float rowv[RL::ROWF];
+#pragma unroll
+                        for (int q = 0; q < RL::ROW_VEC; ++q) { const float4 v4 = __ldcg(src + q); rowv[4 * q] = v4.x; rowv[4 * q + 1] = v4.y; rowv[4 * q + 2] = v4.z; rowv[4 * q + 3] = v4.w; }
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) { w.xs[b * SD + i] = rowv[RL::OFF_S + i]; w.xs2[b * SD + i] = rowv[RL::OFF_S2 + i]; }
+                        w.misc[4 * b] = rowv[RL::OFF_A]; w.misc[4 * b + 1] = rowv[RL::OFF_R]; w.misc[4 * b + 2] = rowv[RL::OFF_D];
+                    }
+                    __syncthreads();
+                    loss = g_td_update(n, w, B, ls, sm, red);
+                    learn_iters += 1;
+                }
+                if (tracing && train_steps < P.trace.cap && tid == 0) {
+                    const int64_t i = train_steps;
+                    P.trace.action[i] = action; P.trace.explore[i] = explore ? 1 : 0;
+                    P.trace.reward[i] = r; P.trace.done[i] = d; P.trace.loss[i] = loss;
+#pragma unroll
+                    for (int k = 0; k < SD; ++k) P.trace.next_state[i * SD + k] = ns[k];
+                }
+                train_steps += 1;
+                if (d > 0.5f) break;
+            }
+            double ep_value;
+            if (c.use_test_env) ep_value = run_test(test_calls++, nullptr, nullptr, test_steps);
+            else ep_value = (double)ep_rew;
+            __syncthreads();
+            if (tid == 0) { lengths[n_ep] = ep_len; rewards[n_ep] = ep_value; __threadfence_block(); }
+            n_ep += 1;
+            __syncthreads();
+            if (episode >= c.init_episodes) {
+                const double avg = mean_window(rewards, n_ep, c.early_out_num, 0);
+                bool solved;
+                if (rule_virtual) {
+                    const double avg_last = mean_window(rewards, n_ep, c.early_out_num, c.early_out_num);
+                    solved = (fabs(avg - avg_last) / (fabs(avg_last) + 1e-9) < c.early_out_virtual_diff) &&
+                             (episode >= c.init_episodes + c.early_out_num);
+                } else solved = avg >= c.solved_reward;
+                if (solved) break;
+            }
+        }
+        double score = 0.0;
+        if (c.final_test)
+            score = run_test(test_calls++, test_rewards, P.test_lengths ? P.test_lengths + (int64_t)lane_id * P.test_stride : nullptr, test_steps);
+        __syncthreads();
+        if (P.q_final) for (int p = tid; p < n.P; p += kGThreads) P.q_final[(int64_t)lane_id * P.q_stride + p] = w.theta[p];
+        if (tid == 0) {
+            le_lane_out o;
+            o.n_episodes = n_ep; o.timed_out = timed_out; o.train_steps = train_steps; o.learn_iters = learn_iters;
+            o.test_steps = test_steps; o.score = score;
+            P.out[lane_id] = o;
+        }
+    }
+}
+
+// unit kernels on caller-owned canonical arrays (same layout as the slot's theta/thetaT/m/v)
+template <int SD, int AD>
+__global__ void __launch_bounds__(kGThreads)
+general_td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, GNet n, float* th, float* thT, float* m, float* v, int32_t* tcount,
+                         int q_stride, const float* __restrict__ rows, int B, float* __restrict__ loss_out, float* scratch,
+                         int64_t scratch_stride) {
+    __shared__ __align__(16) float sm[2 * kGChunk * (kGTile + kGPad)];
+    __shared__ float red[32];
+    const int id = blockIdx.x, tid = threadIdx.x;
+    const le_lane_cfg c = *cfg_dev;
+    int64_t offs[18];
+    gslot_floats(n, 0, 0, B, offs);
+    float* base = scratch + (int64_t)id * scratch_stride;
+    GSlot w;
+    w.ring = nullptr; w.theta = th + (int64_t)id * q_stride; w.thetaT = thT + (int64_t)id * q_stride;
+    w.m = m + (int64_t)id * q_stride; w.v = v + (int64_t)id * q_stride;
+    w.grad = base + offs[5]; w.xs = base + offs[6]; w.xs2 = base + offs[7]; w.misc = base + offs[8]; w.actA = base + offs[9];
+    w.actB = base + offs[10]; w.dact = base + offs[11]; w.q = base + offs[12]; w.q2 = base + offs[13]; w.qT = base + offs[14];
+    w.dq = base + offs[15]; w.obs = base + offs[16]; w.astar = reinterpret_cast<int*>(base + offs[17]);
+    constexpr int ROWP = 2 * SD + 3;
+    const float* my_rows = rows + (int64_t)id * B * ROWP;
+    for (int b = tid; b < B; b += kGThreads) {
+        const float* src = my_rows + (int64_t)b * ROWP;
+#pragma unroll
+        for (int i = 0; i < SD; ++i) { w.xs[b * SD + i] = src[i]; w.xs2[b * SD + i] = src[SD + 1 + i]; }
+        w.misc[4 * b] = src[SD]; w.misc[4 * b + 1] = src[2 * SD + 1]; w.misc[4 * b + 2] = src[2 * SD + 2];
+    }
+    __syncthreads();
+    LearnScalars ls;
+    fill_learn_scalars(ls, c);
+    ls.batch = B;
+    ls.norm = (float)(2.0 / (double)B);
+    const int t0 = tcount[id];
+    ls.b1pow = pow(c.beta1, (double)t0);
+    ls.b2pow = pow(c.beta2, (double)t0);
+    const float loss = g_td_update(n, w, B, ls, sm, red);
+    if (tid == 0) { loss_out[id] = loss; tcount[id] = t0 + 1; }
+}
+
+template <int SD, int AD>
+__global__ void __launch_bounds__(kGThreads)
+general_qnet_forward_kernel(GNet n, const float* __restrict__ q_theta, int q_stride, const float* __restrict__ state,
+                            float* __restrict__ q_out, int32_t* __restrict__ argmax, float* scratch, int64_t scratch_stride) {
+    __shared__ __align__(16) float sm[2 * kGChunk * (kGTile + kGPad)];
+    __shared__ float red[32];
+    const int id = blockIdx.x;
+    float* acts = scratch + (int64_t)id * scratch_stride;
+    float* q = acts + n.sum_out;
+    g_net_forward(n, q_theta + (int64_t)id * q_stride, state + (int64_t)id * SD, SD, 1, acts, sm);
+    g_q_values(n, acts, 1, q, red);
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int k = 0; k < AD; ++k) { q_out[(int64_t)id * AD + k] = q[k]; if (q[k] > q[best]) best = k; }
+        argmax[id] = best;
+    }
+}
+
+}  // namespace le

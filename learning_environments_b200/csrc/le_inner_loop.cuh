@@ -52,7 +52,7 @@ __device__ __forceinline__ double mean_window(const double* vals, int len, int n
     int lo = len - num - ignore_last; if (lo < 0) lo = 0;
     int hi = len - ignore_last; if (hi < 0) hi = 0;
     double s = 0.0;
-    for (int i = lo; i < hi; ++i) s += vals[i];
+    for (int i = lo; i < hi; ++i) s += __ldcg(vals + i);   // written by another thread of this warp/CTA: read through L2
     return s / ((double)(hi - lo) + 1e-9);
 }
 

@@ -24,6 +24,12 @@ _CARTPOLE_SE = {
                      activation_fn="tanh", hidden_size=57, hidden_layer=1, print_rate=10, early_out_num=10,
                      early_out_virtual_diff=0.01),
         "ddqn_vary": dict(vary_hp=True),
+        # default_config_cartpole_syn_env.yaml:58-77
+        "duelingddqn": dict(train_episodes=1000, test_episodes=10, init_episodes=1, batch_size=193, gamma=0.961, lr=0.0091437,
+                            tau=0.07348, eps_init=0.906, eps_min=0.00645, eps_decay=0.8267, rb_size=100000, same_action_num=1,
+                            activation_fn="tanh", hidden_size=61, hidden_layer=1, feature_dim=60, print_rate=1, early_out_num=1,
+                            early_out_virtual_diff=0.01),
+        "duelingddqn_vary": dict(vary_hp=True),
     },
     "envs": {"CartPole-v0": dict(solved_reward=195.0, max_steps=200, activation_fn="leakyrelu", hidden_size=83,
                                  hidden_layer=1, info_dim=0, reward_env_type=0)},
@@ -38,6 +44,12 @@ _ACROBOT_SE = {
                      activation_fn="leakyrelu", hidden_size=112, hidden_layer=1, print_rate=1, early_out_num=10,
                      early_out_virtual_diff=0.01),
         "ddqn_vary": dict(vary_hp=True),
+        # default_config_acrobot.yaml:61-80 (the DuelingDDQN section the transfer evaluations use)
+        "duelingddqn": dict(train_episodes=1000, test_episodes=10, init_episodes=10, batch_size=128, gamma=0.99, lr=1e-3, tau=0.01,
+                            eps_init=1.0, eps_min=0.01, eps_decay=0.9, rb_size=100000, same_action_num=1, activation_fn="relu",
+                            hidden_size=128, hidden_layer=2, feature_dim=128, print_rate=1, early_out_num=10,
+                            early_out_virtual_diff=0.01),
+        "duelingddqn_vary": dict(vary_hp=True),
     },
     "envs": {"Acrobot-v1": dict(solved_reward=-100.0, max_steps=500, activation_fn="prelu", hidden_size=167,
                                 hidden_layer=1, info_dim=0, reward_env_type=0)},

@@ -92,8 +92,8 @@ class GTN_Master(GTN_Base):
         self.verbose = verbose
         if update_mode not in ("replicated", "allreduce"):
             raise ValueError("update_mode must be 'replicated' or 'allreduce'")
-        if self.agent_name.lower() != "ddqn":
-            raise NotImplementedError("GTN inner-loop agent %r is outside the B200 hot path (DDQN is built)" % self.agent_name)
+        if self.agent_name.lower() not in ("ddqn", "duelingddqn"):
+            raise NotImplementedError("GTN inner-loop agent %r is outside the B200 hot path (DDQN / DuelingDDQN are built)" % self.agent_name)
 
         self.time_elapsed_list = [None] * self.num_workers
         self.score_list = [None] * self.num_workers
@@ -133,8 +133,9 @@ class GTN_Master(GTN_Base):
             t = torch.tensor([self.seed], dtype=torch.int64, device=self._coll_device(device))
             dist.broadcast(t, 0)
             self.seed = int(t.item())
-        gamma = config["agents"]["ddqn"]["gamma"]
-        self.lane_cfg = le_config.lane_cfg(config, "ddqn", env_kind, use_test_env=True, final_test=True, step_budget=step_budget,
+        inner = self.agent_name.lower()
+        gamma = config["agents"][inner]["gamma"]
+        self.lane_cfg = le_config.lane_cfg(config, inner, env_kind, use_test_env=True, final_test=True, step_budget=step_budget,
                                            gamma=gamma)
         slopes = self.synthetic_env_orig.env.lane_cfg_fields()["env_slope"]
         for i in range(3):

@@ -32,3 +32,15 @@ def sync_prefix(gold_actions, got_actions):
     n = min(len(gold_actions), len(got_actions))
     neq = np.nonzero(np.asarray(gold_actions[:n]) != np.asarray(got_actions[:n]))[0]
     return int(neq[0]) if neq.size else n
+
+
+def assert_params_close(got, want, lr, what=""):
+    """Adam moves every parameter by <= lr per step whatever the gradient's magnitude, so ulp-level differences in
+    near-zero gradients appear as a small fraction of lr on a few parameters: demand |diff| <= 2% of lr everywhere and
+    5e-5 relative (to the parameter scale, floor 1e-2) on >= 99% of the parameters."""
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    d = np.abs(got - want)
+    assert d.max() <= 0.02 * lr, "%s: max |diff| %.3g exceeds 2%% of lr=%g" % (what, d.max(), lr)
+    rel = d / np.maximum(np.abs(want), 1e-2)
+    assert (rel < 5e-5).mean() >= 0.99, "%s: only %.2f%% of the parameters within 5e-5" % (what, 100 * (rel < 5e-5).mean())

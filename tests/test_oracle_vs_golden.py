@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle, philox
-from tests.helpers import cfg_from_bytes, load_golden, rel_err, sync_prefix
+from tests.helpers import assert_params_close, cfg_from_bytes, load_golden, rel_err, sync_prefix
 
 RTOL = 1e-5
 
@@ -54,12 +54,8 @@ def test_td_update(tag):
         loss, t = c_oracle.td_update(cfg, th, thT, m, v, t, g["rows"][k])
         assert rel_err(loss, g["losses"][k]) < RTOL
         # parameters: 1e-5 relative to the parameter scale (Adam's m/sqrt(v) amplifies ulp noise of tiny gradients)
-        scale = np.maximum(np.abs(g["thetas"][k]), 1e-2)
-        # Adam moves every parameter by <= lr per step whatever the gradient's magnitude, so ulp-level differences in
-        # near-zero gradients show up as a fraction of lr: tolerance 5e-5 (lr 3e-4 .. 3e-3) / 2e-4 (dueling, lr 9e-3)
-        ptol = 2e-4 if "dueling" in tag else 5e-5
-        assert np.max(np.abs(th - g["thetas"][k]) / scale) < ptol
-        assert np.max(np.abs(thT - g["targets"][k]) / scale) < ptol
+        assert_params_close(th, g["thetas"][k], cfg.lr, "theta")
+        assert_params_close(thT, g["targets"][k], cfg.lr, "target")
     assert np.max(np.abs(m - g["adam_m"])) < 1e-5 * max(1.0, np.abs(g["adam_m"]).max())
     assert np.max(np.abs(v - g["adam_v"])) < 1e-5 * max(1.0, np.abs(g["adam_v"]).max())
 
