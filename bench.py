@@ -32,6 +32,9 @@ WORKLOADS = {
     "cartpole_se": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=6),
     "acrobot_se": dict(cfg="acrobot_syn_env", kind="se", members_per_gpu=592, train_episodes=3, init_episodes=1),
     "cartpole_rn": dict(cfg="cartpole_reward_env", kind="rn", members_per_gpu=1184, train_episodes=40),
+    # DuelingDDQN inner loops (general CTA-per-lane kernel): CartPole yaml section, Acrobot section of default_config_acrobot.yaml
+    "cartpole_se_dueling": dict(cfg="cartpole_syn_env", kind="se", agent="duelingddqn", members_per_gpu=296, train_episodes=3),
+    "acrobot_se_dueling": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=148, train_episodes=2, init_episodes=1),
 }
 
 
@@ -40,18 +43,19 @@ def build_lane_cfg(workload):
     from learning_environments_b200._abi import ENV_RN, ENV_SE
     w = WORKLOADS[workload]
     d = default_configs.get(w["cfg"])
-    agent = d["agents"]["ddqn"]
+    name = w.get("agent", "ddqn")
+    agent = d["agents"][name]
     agent["train_episodes"] = w["train_episodes"]
     if "init_episodes" in w:
         agent["init_episodes"] = w["init_episodes"]
-    cfg = config.lane_cfg(d, "ddqn", ENV_SE if w["kind"] == "se" else ENV_RN, use_test_env=True, final_test=True)
+    cfg = config.lane_cfg(d, name, ENV_SE if w["kind"] == "se" else ENV_RN, use_test_env=True, final_test=True)
     return d, cfg
 
 
 def f_step(cfg):
     """Algorithmic flop per inner-loop step: F_env + F_q + 5*B*F_q, F_mlp = sum 2*in*out."""
     from learning_environments_b200._abi import ENV_SE, ENV_RN
-    fq = 2 * (cfg.sd * cfg.q_hidden + cfg.q_hidden * cfg.ad)
+    fq = 2 * sum(i * o for i, o in cfg.q_layer_dims())
     if cfg.env_kind == ENV_SE:
         i, h = cfg.sd + cfg.ad, cfg.env_hidden
         fenv = 2 * (3 * i * h + h * (cfg.sd + 2))
@@ -166,9 +170,10 @@ def run_reference_arm(args):
 
 def workload_config(name, cfg, members_per_gpu, plan):
     w = WORKLOADS[name]
-    c = {"workload": "%s: NES generation, %s, DDQN inner loop (B=%d, Q %d->%d->%d), per lane %d train episodes x <=%d steps "
+    c = {"workload": "%s: NES generation, %s, %s inner loop (B=%d, Q %d->%d->%d), per lane %d train episodes x <=%d steps "
                      "+ per-episode test() of %d real-env episodes + final test()" % (
-                         name, w["cfg"], cfg.batch_size, cfg.sd, cfg.q_hidden, cfg.ad, cfg.train_episodes, cfg.max_steps,
+                         name, w["cfg"], "DuelingDDQN" if cfg.q_kind else "DDQN", cfg.batch_size, cfg.sd, cfg.q_hidden, cfg.ad,
+                         cfg.train_episodes, cfg.max_steps,
                          cfg.test_episodes),
          "members_per_gpu": members_per_gpu, "lanes_per_member": 3, "env_hidden": cfg.env_hidden,
          "l2": "256 MiB buffer written between timed steps (L2 flush)"}

@@ -24,11 +24,11 @@ struct GNet {
     GLayer feat[4], val[2], adv[2];
 };
 
-inline void gnet_add(GLayer* l, int in, int out, int act, int* p, int* y) {
+__host__ __device__ inline void gnet_add(GLayer* l, int in, int out, int act, int* p, int* y) {
     l->in = in; l->out = out; l->act = act; l->w_off = *p; *p += in * out; l->b_off = *p; *p += out; l->y_off = *y; *y += out;
 }
 // same construction as oracle/le_oracle.c build_net (torch state_dict order)
-inline void gnet_build(const le_lane_cfg* c, GNet* n) {
+__host__ __device__ inline void gnet_build(const le_lane_cfg* c, GNet* n) {
     int p = 0, y = 0;
     const int L = c->q_layers > 1 ? c->q_layers : 1, H = c->q_hidden;
     const int act = c->q_act == LE_ACT_TANH ? 1 : 2;
@@ -349,10 +349,11 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
     __shared__ double dred[kGThreads / 32];
     __shared__ int sred[kGThreads / 32];
     __shared__ le_lane_cfg cfg_sm;
+    __shared__ GNet net_sm;          // this lane's network (per-lane q_hidden / q_layers under vary_hp)
     const RunParams& P = G.rp;
-    const GNet& n = G.net;
+    const GNet& n = net_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const GSlot w = gslot_view(G.slots + (int64_t)blockIdx.x * G.slot_stride, n, P.ring_cap, RL::ROWF, G.bmax);
+    const GSlot w = gslot_view(G.slots + (int64_t)blockIdx.x * G.slot_stride, G.net, P.ring_cap, RL::ROWF, G.bmax);   // sized for the maxima (cfg 0)
     for (;;) {
         __syncthreads();
         if (tid == 0) ibox[0] = atomicAdd(P.work_counter, 1);
@@ -366,6 +367,8 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
         }
         __syncthreads();
         const le_lane_cfg& c = cfg_sm;
+        if (tid == 0) gnet_build(&cfg_sm, &net_sm);
+        __syncthreads();
         const uint32_t k0 = P.keys[2 * lane_id], k1 = P.keys[2 * lane_id + 1];
         const float4* pack = P.env_pack + (int64_t)(P.env_index ? P.env_index[lane_id] : 0) * P.env_pack_stride;
         const bool env_tanh = c.env_act == LE_ACT_TANH;

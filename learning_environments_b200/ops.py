@@ -164,13 +164,13 @@ class InnerLoopBuffers(object):
         return o
 
 
-def inner_loop_run(bufs, cfgs, env_theta, env_index, keys, q_init=None, trace_lane=0):
+def inner_loop_run(bufs, cfgs, env_theta, env_index, keys, q_init=None, trace_lane=0, cfg0=None):
     """The fused persistent kernel (le_inner_loop_run): n_lanes complete calc_scores on the current stream.
 
     cfgs: one LaneCfg or a list of n_lanes LaneCfg (per-lane hyper-parameters); env_theta [n_env, P_env] CUDA f32
     (None for ENV_REAL); env_index [n_lanes] int32 or None; keys [n_lanes, 2] (uint32 values in an int64/int32 tensor).
     """
-    cfg0 = bufs.cfg
+    cfg0 = bufs.cfg if cfg0 is None else cfg0     # shapes / strides / kernel set: the maxima under per-lane configurations
     if isinstance(cfgs, LaneCfg):
         cfgs = [cfgs]
     n_cfg = len(cfgs)

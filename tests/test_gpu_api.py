@@ -222,3 +222,27 @@ def test_dueling_ddqn_agent_train_test(le):
     s, a, s2, r, d = rbuf.sample(agent.batch_size)
     want_loss, _ = c_oracle.td_update(agent._unit_cfg(), th, thT, m, v, 0, torch.cat([s, a, s2, r, d], dim=1).numpy())
     assert rel_err(loss.item(), want_loss) < 1e-5
+
+
+def test_vary_hp_batched_agents_match_oracle_per_lane(le):
+    """BASELINE config 4 in miniature: agents with per-lane lr / batch_size / hidden_size / hidden_layer on one SE."""
+    from learning_environments_b200 import vary_hp
+    from learning_environments_b200.rng import lane_keys
+    cfg = le["cfgs"].get("cartpole_syn_env")
+    torch.manual_seed(11)
+    venv = le["envs"].EnvFactory(cfg).generate_virtual_env()
+    theta = venv.env.theta().numpy()
+    over = dict(print_rate=10, early_out_num=2, train_episodes=3, init_episodes=1, test_episodes=2, early_out_virtual_diff=0.01)
+    n = 12
+    rewards, steps, episodes, cfgs = vary_hp.train_test_agents(cfg, theta, agents_num=n, seed=3, overrides=over)
+    assert len({(c.q_hidden, c.batch_size, c.q_layers) for c in cfgs}) > 6          # genuinely heterogeneous lanes
+    assert {c.q_is_register_resident() for c in cfgs} == {True, False}
+    keys = lane_keys(3, 0, np.arange(n), np.zeros(n, int), np.zeros(n, int))
+    ok = 0
+    for i in range(n):
+        want = c_oracle.run_lane(cfgs[i], theta, tuple(int(k) for k in keys[i]))
+        assert len(rewards[i]) == 2 and episodes[i] >= 1
+        if steps[i] == want["train_steps"]:
+            ok += 1
+            assert episodes[i] == want["n_episodes"]
+    assert ok >= 0.7 * n
