@@ -29,9 +29,12 @@ import numpy as np  # noqa: E402
 
 # workload name -> (default_configs name, env kind, members per GPU, bounded train_episodes)
 WORKLOADS = {
-    "cartpole_se": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=6),
+    "cartpole_se": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=10),
     "acrobot_se": dict(cfg="acrobot_syn_env", kind="se", members_per_gpu=592, train_episodes=3, init_episodes=1),
     "cartpole_rn": dict(cfg="cartpole_reward_env", kind="rn", members_per_gpu=1184, train_episodes=40),
+    # BASELINE config 5 (scaling sweep): SE hidden width 1024, 257 lanes per member (theta + 128 x (+eps, -eps) evaluations);
+    # 64 members per GPU = population 512 x 256 envs on 8 GPUs
+    "sweep_h1024": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=64, train_episodes=2, env_hidden=1024, grad_evals=128),
     # DuelingDDQN inner loops (general CTA-per-lane kernel): CartPole yaml section, Acrobot section of default_config_acrobot.yaml
     "cartpole_se_dueling": dict(cfg="cartpole_syn_env", kind="se", agent="duelingddqn", members_per_gpu=296, train_episodes=3),
     "acrobot_se_dueling": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=148, train_episodes=2, init_episodes=1),
@@ -48,8 +51,26 @@ def build_lane_cfg(workload):
     agent["train_episodes"] = w["train_episodes"]
     if "init_episodes" in w:
         agent["init_episodes"] = w["init_episodes"]
+    if "env_hidden" in w:
+        d["envs"][d["env_name"]]["hidden_size"] = w["env_hidden"]
+    if "grad_evals" in w:
+        d["agents"]["gtn"]["num_grad_evals"] = w["grad_evals"]
     cfg = config.lane_cfg(d, name, ENV_SE if w["kind"] == "se" else ENV_RN, use_test_env=True, final_test=True)
     return d, cfg
+
+
+def f_parts(cfg):
+    """(flop per env step without learning, flop per TD update): F_env + F_q and 5*B*F_q."""
+    from learning_environments_b200._abi import ENV_SE, ENV_RN
+    fq = 2 * sum(i * o for i, o in cfg.q_layer_dims())
+    if cfg.env_kind == ENV_SE:
+        i, h = cfg.sd + cfg.ad, cfg.env_hidden
+        fenv = 2 * (3 * i * h + h * (cfg.sd + 2))
+    elif cfg.env_kind == ENV_RN:
+        fenv = 2 * 2 * (cfg.sd * cfg.env_hidden + cfg.env_hidden)
+    else:
+        fenv = 0
+    return fenv + fq, 5 * cfg.batch_size * fq
 
 
 def f_step(cfg):
@@ -175,7 +196,7 @@ def workload_config(name, cfg, members_per_gpu, plan):
                          name, w["cfg"], "DuelingDDQN" if cfg.q_kind else "DDQN", cfg.batch_size, cfg.sd, cfg.q_hidden, cfg.ad,
                          cfg.train_episodes, cfg.max_steps,
                          cfg.test_episodes),
-         "members_per_gpu": members_per_gpu, "lanes_per_member": 3, "env_hidden": cfg.env_hidden,
+         "members_per_gpu": members_per_gpu, "lanes_per_member": 1 + 2 * w.get("grad_evals", 1), "env_hidden": cfg.env_hidden,
          "l2": "256 MiB buffer written between timed steps (L2 flush)"}
     if plan:
         c.update({"resident_warp_slots": plan["slots"], "replay_ring_rows": plan["ring_cap"], "units_per_thread": plan["units"]})
@@ -267,6 +288,7 @@ def main():
     sampler.start()
     ev_pairs = []
     steps_done = 0
+    learn_done = 0
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -275,19 +297,21 @@ def main():
         e1.record()
         ev_pairs.append((e0, e1))
         torch.cuda.synchronize()
-        steps_done += int(ev.bufs.results()["train_steps"].sum())
+        res_k = ev.bufs.results()
+        steps_done += int(res_k["train_steps"].sum())
+        learn_done += int(res_k["learn_iters"].sum())
     barrier()
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev_pairs)
-    t = torch.tensor([dev_ms, float(steps_done)], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, float(steps_done), float(learn_done)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, steps_all = float(tmax[0]), float(tsum[1])
+        dev_ms, steps_all, learn_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
     else:
-        steps_all = float(steps_done)
+        steps_all, learn_all = float(steps_done), float(learn_done)
     value = steps_all / (dev_ms * 1e-3)
 
     # ---------------- end-to-end timing through the host API (e2e) ----------------
@@ -324,7 +348,10 @@ def main():
 
     if rank == 0:
         F = f_step(cfg)
-        achieved = value / world * F / 1e12   # per-GPU TFLOP/s of algorithmic work (fused kernel = the timed region)
+        f_env_q, f_td = f_parts(cfg)
+        # per-GPU TFLOP/s of algorithmic work: every env step costs F_env + F_q, every TD update 5*B*F_q (steps of the
+        # init_episodes do not learn); the fused kernel is >= 95% of the timed region (profiles/)
+        achieved = (steps_all * f_env_q + learn_all * f_td) / world / (dev_ms * 1e-3) / 1e12
         line = {
             "metric": "se_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -337,7 +364,7 @@ def main():
             "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
                          "frac": achieved / ffma_peak if ffma_peak else None,
                          "traffic": _ncu_traffic(steps_all / world / max(args.steps, 1)),
-                         "flop_per_env_step": F, "peak_source": "le_bench_ffma microbenchmark in this run (FP32 FFMA; "
+                         "flop_per_env_step": F, "td_updates_per_env_step": learn_all / max(steps_all, 1.0), "peak_source": "le_bench_ffma microbenchmark in this run (FP32 FFMA; "
                                                                 "MEASURED_PEAKS.json has no FP32 figure)",
                          "hbm": {"algorithmic_bytes_per_env_step": (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4,
                                  "achieved_gbs": value / world * (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4 / 1e9,

@@ -252,3 +252,30 @@ def test_general_kernel_many_lanes_vs_oracle(ops):
     same = res["train_steps"] == oracle["train_steps"]
     assert same.mean() >= 0.6, (res["train_steps"], oracle["train_steps"])
     assert np.array_equal(res["learn_iters"][same], oracle["learn_iters"][same])
+
+
+def test_wide_synthetic_env_h1024_scaling_sweep_shape(ops):
+    """BASELINE config 5 shape: SE hidden width 1024 (27 654 parameters), many lanes per member."""
+    g = load_golden("trajectory_cartpole_se.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    cfg.env_hidden = 1024
+    cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 2, 2, 1
+    P = cfg.se_params()
+    assert P == 27654
+    rng = np.random.RandomState(8)
+    pop, lanes = 2, 6
+    thetas = (rng.uniform(-1, 1, size=(pop, P)) * 0.05).astype(np.float32)
+    states = rng.uniform(-1, 1, size=(pop * lanes, 4)).astype(np.float32)
+    actions = rng.randint(0, 2, size=pop * lanes).astype(np.int32)
+    ns, r, d = ops.se_forward(cfg, dev(thetas), dev(states), dev(actions), lanes_per_member=lanes)
+    ns, r, d = ns.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+    for i in range(pop * lanes):
+        ons, orr, od = c_oracle.se_step(cfg, thetas[i // lanes], states[i], actions[i])
+        assert rel_err(ns[i], ons, 1e-2) < RTOL and rel_err(r[i], orr, 1e-2) < RTOL and rel_err(d[i], od, 1e-2) < RTOL
+    keys = [philox.lane_key(2, 0, i // lanes, 0, i % lanes) for i in range(pop * lanes)]
+    env_index = np.arange(pop * lanes, dtype=np.int32) // lanes
+    bufs = _run_fused(ops, cfg, thetas, keys, None, n_env=pop, env_index=env_index)
+    res = bufs.results()
+    oracle = c_oracle.run_lanes(cfg, thetas, env_index, np.array(keys, np.uint32), n_threads=6)
+    assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0])
+    assert (res["train_steps"] == oracle["train_steps"]).mean() >= 0.75
