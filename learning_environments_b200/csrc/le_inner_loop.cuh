@@ -35,7 +35,8 @@ template <int SD, int AD, int U>
 struct SmemWarp {
     using SL = StageLayout<SD>;
     static constexpr int PUP = ((SD + 1 + AD) + 3) / 4 * 4;  // padded per-unit record of the test-phase weight image
-    static constexpr int STAGE_F = SL::ROWS * SL::STAGE_F;
+    static constexpr int STAGE_ONE_F = SL::ROWS * SL::STAGE_F;
+    static constexpr int STAGE_F = 2 * STAGE_ONE_F;   // double buffer: the gather of round k+1 overlaps the compute of round k
     static constexpr int QW_F = U * 32 * PUP;
     static constexpr int BUF_F = STAGE_F > QW_F ? STAGE_F : QW_F;
     static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
@@ -56,19 +57,21 @@ __device__ __forceinline__ double mean_window(const double* vals, int len, int n
     return s / ((double)(hi - lo) + 1e-9);
 }
 
-// One replay row (HBM layout RowLayout) -> stage layout: inputs duplicated for FFMA2, action as int bits.
+// One replay row (registers, HBM layout) -> shared-memory stage (same layout)
 template <int SD>
 __device__ __forceinline__ void stage_row(float* dst, const float (&rowv)[RowLayout<SD>::ROWF]) {
     using RL = RowLayout<SD>;
-    using SL = StageLayout<SD>;
     float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-    for (int i = 0; i < SD; i += 2) {
-        d4[(SL::OFF_S + 2 * i) / 4] = make_float4(rowv[RL::OFF_S + i], rowv[RL::OFF_S + i], rowv[RL::OFF_S + i + 1], rowv[RL::OFF_S + i + 1]);
-        d4[(SL::OFF_S2 + 2 * i) / 4] = make_float4(rowv[RL::OFF_S2 + i], rowv[RL::OFF_S2 + i], rowv[RL::OFF_S2 + i + 1], rowv[RL::OFF_S2 + i + 1]);
-    }
-    d4[SL::OFF_A / 4] = make_float4(__int_as_float((int)rowv[RL::OFF_A]), rowv[RL::OFF_R], rowv[RL::OFF_D], 0.f);
+    for (int q = 0; q < RL::ROW_VEC; ++q) d4[q] = make_float4(rowv[4 * q], rowv[4 * q + 1], rowv[4 * q + 2], rowv[4 * q + 3]);
 }
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int SD, int AD, int U, int ACT>
 struct FusedLane {
@@ -242,33 +245,41 @@ struct FusedLane {
                     core.zero_grads();
                     float loss_part = 0.f;
                     const int B = ls.batch;
-                    for (int sc = 0; sc * SL::ROWS < B; ++sc) {
+                    // replay_buffer.sample: idx = randint(0, size, B) on the P_SAMPLE stream (utils.py:35).  Thread t < 16
+                    // gathers the 4 rows of Philox block (round*16 + t) with 16-byte cp.async (global -> shared, no
+                    // registers); round k+1 is in flight while round k is computed.
+                    const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(smem);
+                    auto gather = [&](int sc, int buf) {
                         const int nrows = min(SL::ROWS, B - sc * SL::ROWS);
                         const int nfill = (nrows + Core::R - 1) / Core::R * Core::R;
-                        // replay_buffer.sample: idx = randint(0, size, B) on the P_SAMPLE stream (utils.py:35);
-                        // thread t gathers the 4 rows of Philox block (sc*ROWS/4 + t) and stages them input-duplicated
-                        const int blk = sc * (SL::ROWS / 4) + lane;
                         if (4 * lane < nfill) {
-                            const u32x4 w = philox4x32_10((uint32_t)learn_iters, (uint32_t)blk, LE_P_SAMPLE, 0u, k0, k1);
-                            float4 v[4][RL::ROW_VEC];
+                            const u32x4 w = philox4x32_10((uint32_t)learn_iters, (uint32_t)(sc * (SL::ROWS / 4) + lane), LE_P_SAMPLE, 0u, k0, k1);
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                const bool ok = 4 * lane + kk < nrows;
-                                const uint32_t idx = __umulhi(pick(w, kk), (uint32_t)rb_size);
-                                const float4* src = reinterpret_cast<const float4*>(ring + (int64_t)idx * RL::ROWF);
+                                const int rr = 4 * lane + kk;
+                                const uint32_t dst = stage_sa + (uint32_t)((buf * SW::STAGE_ONE_F + rr * SL::STAGE_F) * 4);
+                                if (rr < nrows) {
+                                    const uint32_t idx = __umulhi(pick(w, kk), (uint32_t)rb_size);
+                                    const float* src = ring + (int64_t)idx * RL::ROWF;
 #pragma unroll
-                                for (int q = 0; q < RL::ROW_VEC; ++q) v[kk][q] = ok ? ld_cg_f4(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
+                                    for (int q = 0; q < RL::ROW_VEC; ++q) cp_async16(dst + 16 * q, src + 4 * q);
+                                } else {
+                                    float4* z = reinterpret_cast<float4*>(smem + buf * SW::STAGE_ONE_F + rr * SL::STAGE_F);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                float rowv[RL::ROWF];
-#pragma unroll
-                                for (int q = 0; q < RL::ROW_VEC; ++q) { rowv[4 * q] = v[kk][q].x; rowv[4 * q + 1] = v[kk][q].y; rowv[4 * q + 2] = v[kk][q].z; rowv[4 * q + 3] = v[kk][q].w; }
-                                stage_row<SD>(smem + (4 * lane + kk) * SL::STAGE_F, rowv);
+                                    for (int q = 0; q < RL::ROW_VEC; ++q) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
                             }
                         }
+                        cp_async_commit();
+                    };
+                    const int n_rounds = (B + SL::ROWS - 1) / SL::ROWS;
+                    gather(0, 0);
+                    for (int sc = 0; sc < n_rounds; ++sc) {
+                        const int nrows = min(SL::ROWS, B - sc * SL::ROWS);
+                        if (sc + 1 < n_rounds) { gather(sc + 1, (sc + 1) & 1); cp_async_wait<1>(); }
+                        else cp_async_wait<0>();
                         __syncwarp();
-                        loss_part += core.td_rows(smem, smem + SW::OFF_RED, nrows, ls, lane);
+                        loss_part += core.td_rows(smem + (sc & 1) * SW::STAGE_ONE_F, smem + SW::OFF_RED, nrows, ls, lane);
                         __syncwarp();
                     }
                     loss = warp_allreduce_sum(loss_part) / (float)B;
