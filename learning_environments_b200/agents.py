@@ -213,7 +213,7 @@ class DDQN(BaseAgent):
         off_s2 = sd if tail else sd + 2
         rb._alloc(max(n, 1))
         rb.state[:n] = ring[:, 0:sd]
-        rb.action[:n, 0] = ring[:, off_a]
+        rb.action[:n, 0] = ring[:, off_a].contiguous().view(torch.int32).float()   # the ring stores the action's int32 bits
         rb.next_state[:n] = ring[:, off_s2:off_s2 + sd]
         rb.reward[:n, 0] = ring[:, off_a + 1]
         rb.done[:n, 0] = ring[:, 2 * sd + 2]

@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
                     for (int i = 0; i < RL::ROWF; ++i) rowv[i] = 0.f;
 #pragma unroll
                     for (int i = 0; i < SD; ++i) { rowv[RL::OFF_S + i] = state[i]; rowv[RL::OFF_S2 + i] = ns[i]; }
-                    rowv[RL::OFF_A] = (float)action; rowv[RL::OFF_R] = r; rowv[RL::OFF_D] = d;
+                    rowv[RL::OFF_A] = __int_as_float(action); rowv[RL::OFF_R] = r; rowv[RL::OFF_D] = d;
                     float4* dst = reinterpret_cast<float4*>(w.ring + (int64_t)rb_ptr * RL::ROWF);
 #pragma unroll
                     for (int q = 0; q < RL::ROW_VEC; ++q)
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
                         for (int q = 0; q < RL::ROW_VEC; ++q) { const float4 v4 = __ldcg(src + q); rowv[4 * q] = v4.x; rowv[4 * q + 1] = v4.y; rowv[4 * q + 2] = v4.z; rowv[4 * q + 3] = v4.w; }
 #pragma unroll
                         for (int i = 0; i < SD; ++i) { w.xs[b * SD + i] = rowv[RL::OFF_S + i]; w.xs2[b * SD + i] = rowv[RL::OFF_S2 + i]; }
-                        w.misc[4 * b] = rowv[RL::OFF_A]; w.misc[4 * b + 1] = rowv[RL::OFF_R]; w.misc[4 * b + 2] = rowv[RL::OFF_D];
+                        w.misc[4 * b] = (float)__float_as_int(rowv[RL::OFF_A]); w.misc[4 * b + 1] = rowv[RL::OFF_R]; w.misc[4 * b + 2] = rowv[RL::OFF_D];
                     }
                     __syncthreads();
                     loss = g_td_update(n, w, B, ls, sm, red);

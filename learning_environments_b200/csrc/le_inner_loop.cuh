@@ -226,7 +226,7 @@ struct FusedLane {
                     for (int i = 0; i < RL::ROWF; ++i) rowv[i] = 0.f;
 #pragma unroll
                     for (int i = 0; i < SD; ++i) { rowv[RL::OFF_S + i] = state[i]; rowv[RL::OFF_S2 + i] = ns[i]; }
-                    rowv[RL::OFF_A] = (float)action; rowv[RL::OFF_R] = r; rowv[RL::OFF_D] = d;
+                    rowv[RL::OFF_A] = __int_as_float(action); rowv[RL::OFF_R] = r; rowv[RL::OFF_D] = d;
                     float4* dst = reinterpret_cast<float4*>(ring + (int64_t)rb_ptr * RL::ROWF);
 #pragma unroll
                     for (int q = 0; q < RL::ROW_VEC; ++q)

@@ -136,7 +136,7 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
             if (rr < nrows) {
 #pragma unroll
                 for (int i = 0; i < SD; ++i) { rowv[RL::OFF_S + i] = src[i]; rowv[RL::OFF_S2 + i] = src[SD + 1 + i]; }
-                rowv[RL::OFF_A] = src[SD]; rowv[RL::OFF_R] = src[2 * SD + 1]; rowv[RL::OFF_D] = src[2 * SD + 2];
+                rowv[RL::OFF_A] = __int_as_float((int)src[SD]); rowv[RL::OFF_R] = src[2 * SD + 1]; rowv[RL::OFF_D] = src[2 * SD + 2];
             }
             stage_row<SD>(smem + rr * SL::STAGE_F, rowv);
         }
