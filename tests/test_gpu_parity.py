@@ -279,3 +279,65 @@ def test_wide_synthetic_env_h1024_scaling_sweep_shape(ops):
     oracle = c_oracle.run_lanes(cfg, thetas, env_index, np.array(keys, np.uint32), n_threads=6)
     assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0])
     assert (res["train_steps"] == oracle["train_steps"]).mean() >= 0.75
+
+
+def _edge_cfg(**over):
+    g = load_golden("trajectory_cartpole_se.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 4, 3, 1
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg, g["env_theta"]
+
+
+@pytest.mark.parametrize("name,over", [
+    ("ring_wraps", dict(rb_size=37)),                         # replay ring smaller than the run: ptr wraps, size saturates
+    ("tiny_batch", dict(batch_size=1)),                       # B = 1 (a chunk with 7 padded rows)
+    ("odd_batch", dict(batch_size=67)),                       # B not a multiple of the 8-row chunk or the 64-row round
+    ("big_batch", dict(batch_size=597)),                      # upper end of DDQN_vary's batch range: 10 gather rounds
+    ("narrow_net", dict(q_hidden=19)),                        # fewer hidden units than lanes (masked units stay zero)
+    ("relu", dict(q_act=1)),                                  # nn.ReLU Q-net
+    ("leaky", dict(q_act=2)),
+    ("many_test_episodes", dict(test_episodes=40)),           # more test episodes than threads in a warp: two passes
+    ("step_budget", dict(step_budget=150)),                   # time_is_up analog: stops before an episode starts
+    ("no_test_env", dict(use_test_env=0, early_out_num=1)),   # virtual-env plateau early-out rule
+    ("init_only", dict(init_episodes=9)),                     # never learns: pure acting / replay filling
+    ("solved_early_out", dict(solved_reward=5.0)),            # real-env early-out fires after the first learning episode
+])
+def test_fused_edge_cases_vs_oracle(ops, name, over):
+    cfg, theta = _edge_cfg(**over)
+    keys = [philox.lane_key(21, 0, i, 0, 0) for i in range(6)]
+    bufs = _run_fused(ops, cfg, theta, keys, None)
+    res = bufs.results()
+    oracle = c_oracle.run_lanes(cfg, theta, None, np.array(keys, np.uint32), n_threads=6)
+    assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0]), name       # pre-learning episode: exact
+    same = (res["train_steps"] == oracle["train_steps"]) & (res["n_episodes"] == oracle["n_episodes"])
+    assert same.mean() >= 0.66, (name, res["train_steps"], oracle["train_steps"])
+    assert np.array_equal(res["learn_iters"][same], oracle["learn_iters"][same]), name
+    assert np.array_equal(res["timed_out"][same], oracle["timed_out"][same]), name
+    assert np.array_equal(res["test_steps"][same], oracle["test_steps"][same]) or np.isclose(res["score"][same], oracle["score"][same]).mean() >= 0.6, name
+    if name in ("step_budget", "init_only", "solved_early_out"):
+        assert same.all(), name        # no learning-driven chaos before the stop: bookkeeping must be exact
+        assert np.allclose(res["score"], oracle["score"]) or name == "step_budget"
+    if name == "step_budget":
+        assert res["timed_out"].all() and (res["train_steps"] >= 150).all()
+    if name == "solved_early_out":
+        assert (res["n_episodes"] == 2).all()
+
+
+def test_general_kernel_edge_cases_vs_oracle(ops):
+    g = load_golden("trajectory_cartpole_se_dueling.npz")
+    for over in (dict(rb_size=41, batch_size=70), dict(test_episodes=70, train_episodes=2), dict(step_budget=120),
+                 dict(q_kind=0, q_layers=2, q_hidden=150, q_feature_dim=0, q_act=1)):
+        cfg = cfg_from_bytes(g["cfg"])
+        cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 3, 2, 1
+        for k, v in over.items():
+            setattr(cfg, k, v)
+        keys = [philox.lane_key(22, 0, i, 0, 0) for i in range(3)]
+        bufs = _run_fused(ops, cfg, g["env_theta"], keys, None)
+        res = bufs.results()
+        oracle = c_oracle.run_lanes(cfg, g["env_theta"], None, np.array(keys, np.uint32), n_threads=3)
+        assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0]), over
+        same = res["train_steps"] == oracle["train_steps"]
+        assert same.mean() >= 0.66, (over, res["train_steps"], oracle["train_steps"])
+        assert np.array_equal(res["timed_out"], oracle["timed_out"]), over
