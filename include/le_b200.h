@@ -96,7 +96,7 @@ typedef struct le_lane_cfg {
     int32_t q_kind;         /* LE_Q_DQN (models/actor_critic.py:84-91) | LE_Q_DUELING (:94-122)                */
     int32_t q_layers;       /* hidden_layer of the Q-net / feature stream (0 and 1 build the same net)         */
     int32_t q_feature_dim;  /* Critic_DuelingDQN feature_dim (heads: fd -> fd -> {1, ad})                      */
-    int32_t reserved0;
+    int32_t same_action_num; /* agent same_action_num (envs/env_wrapper.py:24-61, agents/base_agent.py:104,123); 0 == 1 */
 } le_lane_cfg;
 
 /* Per-lane results (what train()/test() return, as arrays). */

@@ -33,7 +33,7 @@ class LaneCfg(C.Structure):
         ("eps_init", C.c_double), ("eps_min", C.c_double), ("eps_decay", C.c_double),
         ("early_out_virtual_diff", C.c_double), ("solved_reward", C.c_double),
         ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
-        ("q_kind", C.c_int32), ("q_layers", C.c_int32), ("q_feature_dim", C.c_int32), ("reserved0", C.c_int32),
+        ("q_kind", C.c_int32), ("q_layers", C.c_int32), ("q_feature_dim", C.c_int32), ("same_action_num", C.c_int32),
     ]
 
     def copy(self):

@@ -131,8 +131,6 @@ class DDQN(BaseAgent):
         self.feature_dim = int(c.get("feature_dim", 0)) if self._Q_KIND == Q_DUELING else 0
         if self.hidden_layer > 2:
             raise NotImplementedError("Q-nets with hidden_layer > 2 are outside the compiled kernel set")
-        if int(c.get("same_action_num", 1)) != 1:
-            raise NotImplementedError("same_action_num != 1 is outside the compiled kernel set")
         self._act_id = ACT_IDS[str(c["activation_fn"])]
         self._env_name = config["env_name"]
         dev = _cuda_device()
@@ -169,6 +167,7 @@ class DDQN(BaseAgent):
         c.train_episodes, c.test_episodes, c.init_episodes = int(train_episodes), int(self.test_episodes), int(self.init_episodes)
         c.max_steps = int(env.max_episode_steps())
         c.early_out_num = int(self.early_out_num)
+        c.same_action_num = max(int(self.same_action_num), 1)
         c.use_test_env = 1 if test_env is not None else 0
         c.final_test = 1 if final_test else 0
         budget = int(self.step_budget)

@@ -39,8 +39,9 @@ def lane_cfg(config, agent_name="ddqn", env_kind=ENV_SE, use_test_env=True, fina
         raise NotImplementedError("SE/RN nets with hidden_layer > 1 are outside the compiled kernel set")
     if int(a.get("hidden_layer", 1)) > 2:
         raise NotImplementedError("Q-nets with hidden_layer > 2 are outside the compiled kernel set")
-    if int(a.get("same_action_num", 1)) != 1:
-        raise NotImplementedError("same_action_num != 1 is outside the compiled kernel set")
+    if int(a.get("same_action_num", 1)) < 1:
+        raise ValueError("same_action_num must be >= 1")
+    c.same_action_num = int(a.get("same_action_num", 1))
     c.env_hidden = int(e.get("hidden_size", 0))
     c.env_act = ACT_IDS[str(e.get("activation_fn", "identity"))]
     slope = 0.25 if c.env_act == ACT_IDS["prelu"] else 0.01

@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
 #pragma unroll
                     for (int i = 0; i < SD; ++i) w.obs[tid * SD + i] = obs[i];
                 }
-                for (int t = 0; t < c.max_steps; ++t) {
+                const int K = c.same_action_num > 1 ? c.same_action_num : 1;
+                for (int t = 0; t < c.max_steps; t += K) {
                     if (!__syncthreads_or(running ? 1 : 0)) break;
                     g_net_forward(n, w.theta, w.obs, SD, M, w.actB, sm);
                     g_q_values(n, w.actB, M, w.q2, red);
@@ -415,6 +416,15 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
                             if (w.q2[tid * AD + k] > w.q2[tid * AD + best]) best = k;
                         float r, d;
                         real_step<SD>(c.real_env, c.max_steps, st, elapsed, best, obs, r, d);
+                        if (K > 1) {
+                            double rsum = (double)r;
+                            for (int k = 1; k < K && !(d > 0.5f); ++k) {
+                                float rk;
+                                real_step<SD>(c.real_env, c.max_steps, st, elapsed, best, obs, rk, d);
+                                rsum += (double)rk;
+                            }
+                            r = (float)rsum;
+                        }
 #pragma unroll
                         for (int i = 0; i < SD; ++i) w.obs[tid * SD + i] = obs[i];
                         ep_rew += r;
@@ -458,7 +468,8 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
             real_obs<SD>(c.real_env, st, state);
             int elapsed = 0, ep_len = 0;
             float ep_rew = 0.f;
-            for (int t = 0; t < c.max_steps; ++t) {
+            const int K = c.same_action_num > 1 ? c.same_action_num : 1;
+            for (int t = 0; t < c.max_steps; t += K) {
                 const u32x4 wa = philox4x32_10((uint32_t)train_steps, 0u, LE_P_ACT, 0u, k0, k1);
                 const bool explore = ((double)(wa.x >> 8) * (1.0 / 16777216.0)) < eps;
                 int action;
@@ -469,12 +480,20 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
                     __syncthreads();
                     action = g_greedy_row(n, w, box, sm, red, ibox);
                 }
-                float ns[SD], r, d;
+                float ns[SD], r = 0.f, d = 0.f;
                 if (c.env_kind == LE_ENV_SE) {
                     __syncthreads();
-                    if (warp == 0) {
-                        float ns0[SD], r0, d0;
-                        se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, state, action, lane, ns0, r0, d0);
+                    if (warp == 0) {   // same_action_num chained SE steps, fp32 reward sum (envs/env_wrapper.py:24-30)
+                        float cur[SD], ns0[SD], r0 = 0.f, d0 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) cur[i] = state[i];
+                        for (int k = 0; k < K; ++k) {
+                            float rk;
+                            se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, cur, action, lane, ns0, rk, d0);
+                            r0 = k == 0 ? rk : r0 + rk;
+#pragma unroll
+                            for (int i = 0; i < SD; ++i) cur[i] = ns0[i];
+                        }
                         if (lane == 0) {
 #pragma unroll
                             for (int i = 0; i < SD; ++i) box[i] = ns0[i];
@@ -486,20 +505,31 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
                     for (int i = 0; i < SD; ++i) ns[i] = box[i];
                     r = box[SD]; d = box[SD + 1];
                     __syncthreads();
-                } else {
-                    float rr;
-                    real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
-                    if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
-                        __syncthreads();
-                        if (warp == 0) {
-                            float ps, ps2;
-                            rn_phi2<SD>(pack, c.env_hidden, env_tanh, state, ns, lane, ps, ps2);
-                            if (lane == 0) box[0] = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
-                        }
-                        __syncthreads();
-                        r = box[0];
-                        __syncthreads();
-                    } else r = rr;
+                } else {   // real branch: python-float reward sum, break on done (envs/env_wrapper.py:56-61)
+                    float cur[SD];
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) cur[i] = state[i];
+                    double rsum = 0.0;
+                    for (int k = 0; k < K; ++k) {
+                        float rr, rk;
+                        real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
+                        if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
+                            __syncthreads();
+                            if (warp == 0) {
+                                float ps, ps2;
+                                rn_phi2<SD>(pack, c.env_hidden, env_tanh, cur, ns, lane, ps, ps2);
+                                if (lane == 0) box[0] = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
+                            }
+                            __syncthreads();
+                            rk = box[0];
+                            __syncthreads();
+                        } else rk = rr;
+                        rsum += (double)rk;
+                        r = K == 1 ? rk : (float)rsum;
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) cur[i] = ns[i];
+                        if (d > 0.5f) break;
+                    }
                 }
                 {   // replay_buffer.add
                     float rowv[RL::ROWF];
@@ -518,7 +548,7 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
 #pragma unroll
                 for (int i = 0; i < SD; ++i) state[i] = ns[i];
                 ep_rew += r;
-                ep_len += 1;
+                ep_len += K;
                 float loss = __int_as_float(0x7fc00000);
                 if (episode >= c.init_episodes) {
                     __syncthreads();

@@ -109,7 +109,8 @@ struct FusedLane {
             float ep_rew = 0.f;
             int ep_steps = 0;
             bool running = active;
-            for (int t = 0; t < c.max_steps; ++t) {
+            const int K = c.same_action_num > 1 ? c.same_action_num : 1;
+            for (int t = 0; t < c.max_steps; t += K) {   // agents/base_agent.py:193
                 if (!__any_sync(LE_FULL_MASK, running)) break;
                 if (running) {
                     float q[AD];
@@ -129,6 +130,15 @@ struct FusedLane {
                     const int act = Core::argmax_first(q);  // select_test_action agents/DDQN.py:106-110
                     float r, d;
                     real_step<SD>(c.real_env, c.max_steps, st, elapsed, act, obs, r, d);
+                    if (K > 1) {   // EnvWrapper.step real branch (envs/env_wrapper.py:56-61): python-float reward sum, break on done
+                        double rsum = (double)r;
+                        for (int k = 1; k < K && !(d > 0.5f); ++k) {
+                            float rk;
+                            real_step<SD>(c.real_env, c.max_steps, st, elapsed, act, obs, rk, d);
+                            rsum += (double)rk;
+                        }
+                        r = (float)rsum;
+                    }
                     ep_rew += r;
                     steps += 1;
                     ep_steps += 1;
@@ -195,7 +205,8 @@ struct FusedLane {
             real_obs<SD>(c.real_env, st, state);
             int elapsed = 0, ep_len = 0;
             float ep_rew = 0.f;
-            for (int t = 0; t < c.max_steps; ++t) {
+            const int K = c.same_action_num > 1 ? c.same_action_num : 1;
+            for (int t = 0; t < c.max_steps; t += K) {   // agents/base_agent.py:104
                 // ---- select_train_action (agents/DDQN.py:97-104)
                 const u32x4 wa = philox4x32_10((uint32_t)train_steps, 0u, LE_P_ACT, 0u, k0, k1);
                 const bool explore = ((double)(wa.x >> 8) * (1.0 / 16777216.0)) < eps;
@@ -210,14 +221,35 @@ struct FusedLane {
                 float ns[SD], r, d;
                 if (c.env_kind == LE_ENV_SE) {
                     se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, state, action, lane, ns, r, d);
+                    // same_action_num > 1 (envs/env_wrapper.py:24-30): chained SE steps, fp32 reward sum, no break on done
+                    for (int k = 1; k < K; ++k) {
+                        float cur[SD], rk;
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) cur[i] = ns[i];
+                        se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, cur, action, lane, ns, rk, d);
+                        r += rk;
+                    }
                 } else {
-                    float rr;
-                    real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
-                    if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
-                        float ps, ps2;
-                        rn_phi2<SD>(pack, c.env_hidden, env_tanh, state, ns, lane, ps, ps2);
-                        r = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
-                    } else r = rr;
+                    // real branch (envs/env_wrapper.py:56-61): python-float reward sum over same_action_num steps, break on done
+                    float cur[SD];
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) cur[i] = state[i];
+                    double rsum = 0.0;
+                    for (int k = 0; k < K; ++k) {
+                        float rr, rk;
+                        real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
+                        if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
+                            float ps, ps2;
+                            rn_phi2<SD>(pack, c.env_hidden, env_tanh, cur, ns, lane, ps, ps2);
+                            rk = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
+                        } else rk = rr;
+                        if (K == 1) { r = rk; break; }
+                        rsum += (double)rk;
+                        r = (float)rsum;
+#pragma unroll
+                        for (int i = 0; i < SD; ++i) cur[i] = ns[i];
+                        if (d > 0.5f) break;
+                    }
                 }
                 // ---- replay_buffer.add (utils.py:24-32): row [s a s' r d] in the 16B-aligned layout RL
                 {
@@ -237,7 +269,7 @@ struct FusedLane {
 #pragma unroll
                 for (int i = 0; i < SD; ++i) state[i] = ns[i];
                 ep_rew += r;
-                ep_len += 1;
+                ep_len += K;   // episode_length += same_action_num (agents/base_agent.py:123)
                 // ---- learn (agents/DDQN.py:60-95)
                 float loss = __int_as_float(0x7fc00000);
                 if (episode >= c.init_episodes) {

@@ -320,30 +320,53 @@ def gen_nes(seed):
 
 
 def main():
+    """python oracle/gen_golden.py [name ...] — regenerates all fixtures, or only those whose name contains an argument."""
     os.makedirs(GOLDEN, exist_ok=True)
     import torch
     torch.set_num_threads(1)
-    gen_se_step("default_config_cartpole_syn_env.yaml", "cartpole", 1)
-    gen_se_step("default_config_acrobot_syn_env.yaml", "acrobot", 2)
-    gen_rn_reward(3)
-    gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole", 4)
-    gen_td_update("default_config_acrobot_syn_env.yaml", "acrobot", 5)
-    gen_td_update("default_config_cartpole_reward_env.yaml", "cartpole_rn", 6)
-    gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole_dueling", 8, agent="DuelingDDQN")
-    gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")
-    gen_td_update("default_config_cartpole_syn_env.yaml", "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)
-    gen_real_env(7)
-    gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se", 11, (0x1234, 0xABCD), "se",
-                   dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)
-    gen_trajectory("default_config_acrobot_syn_env.yaml", "acrobot_se", 12, (0x77, 0x99), "se",
-                   dict(train_episodes=4, test_episodes=2, init_episodes=1), trace_cap=800)
-    gen_trajectory("default_config_cartpole_reward_env.yaml", "cartpole_rn", 13, (0x5, 0x6), "rn",
-                   dict(train_episodes=12, test_episodes=1, init_episodes=2), trace_cap=300)
-    gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se_notest", 14, (0x42, 0x43), "se",
-                   dict(train_episodes=8, test_episodes=3, init_episodes=2, early_out_num=2), trace_cap=200, use_test_env=False)
-    gen_trajectory("default_config_cartpole_syn_env.yaml", "cartpole_se_dueling", 15, (0x51, 0x52), "se",
-                   dict(train_episodes=3, test_episodes=2, init_episodes=1), trace_cap=300, agent="DuelingDDQN")
-    gen_nes(21)
+    CP, AC, RN = "default_config_cartpole_syn_env.yaml", "default_config_acrobot_syn_env.yaml", "default_config_cartpole_reward_env.yaml"
+    jobs = [
+        ("se_step_cartpole", lambda: gen_se_step(CP, "cartpole", 1)),
+        ("se_step_acrobot", lambda: gen_se_step(AC, "acrobot", 2)),
+        ("rn_reward_cartpole", lambda: gen_rn_reward(3)),
+        ("td_update_cartpole", lambda: gen_td_update(CP, "cartpole", 4)),
+        ("td_update_acrobot", lambda: gen_td_update(AC, "acrobot", 5)),
+        ("td_update_cartpole_rn", lambda: gen_td_update(RN, "cartpole_rn", 6)),
+        ("td_update_cartpole_dueling", lambda: gen_td_update(CP, "cartpole_dueling", 8, agent="DuelingDDQN")),
+        ("td_update_acrobot_dueling", lambda: gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")),
+        ("td_update_cartpole_ddqn_l2", lambda: gen_td_update(CP, "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)),
+        ("real_env", lambda: gen_real_env(7)),
+        ("trajectory_cartpole_se", lambda: gen_trajectory(CP, "cartpole_se", 11, (0x1234, 0xABCD), "se",
+                                                          dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)),
+        ("trajectory_acrobot_se", lambda: gen_trajectory(AC, "acrobot_se", 12, (0x77, 0x99), "se",
+                                                         dict(train_episodes=4, test_episodes=2, init_episodes=1), trace_cap=800)),
+        ("trajectory_cartpole_rn", lambda: gen_trajectory(RN, "cartpole_rn", 13, (0x5, 0x6), "rn",
+                                                          dict(train_episodes=12, test_episodes=1, init_episodes=2), trace_cap=300)),
+        ("trajectory_cartpole_se_notest", lambda: gen_trajectory(CP, "cartpole_se_notest", 14, (0x42, 0x43), "se",
+                                                                 dict(train_episodes=8, test_episodes=3, init_episodes=2, early_out_num=2),
+                                                                 trace_cap=200, use_test_env=False)),
+        ("trajectory_cartpole_se_dueling", lambda: gen_trajectory(CP, "cartpole_se_dueling", 15, (0x51, 0x52), "se",
+                                                                  dict(train_episodes=3, test_episodes=2, init_episodes=1), trace_cap=300,
+                                                                  agent="DuelingDDQN")),
+        # same_action_num > 1 (envs/env_wrapper.py:24-61; agents/base_agent.py:104,123) on all three env branches, and
+        # training directly on the real env (experiments/syn_env_run_vary_hp.py mode 0)
+        ("trajectory_cartpole_se_k2", lambda: gen_trajectory(CP, "cartpole_se_k2", 16, (0x61, 0x62), "se",
+                                                             dict(train_episodes=5, test_episodes=3, init_episodes=1, same_action_num=2),
+                                                             trace_cap=300)),
+        ("trajectory_cartpole_rn_k3", lambda: gen_trajectory(RN, "cartpole_rn_k3", 17, (0x63, 0x64), "rn",
+                                                             dict(train_episodes=12, test_episodes=2, init_episodes=2, same_action_num=3),
+                                                             trace_cap=300)),
+        ("trajectory_cartpole_real_k2", lambda: gen_trajectory(CP, "cartpole_real_k2", 18, (0x65, 0x66), "real",
+                                                               dict(train_episodes=10, test_episodes=2, init_episodes=2, same_action_num=2),
+                                                               trace_cap=300)),
+        ("trajectory_acrobot_real", lambda: gen_trajectory(AC, "acrobot_real", 19, (0x67, 0x68), "real",
+                                                           dict(train_episodes=2, test_episodes=1, init_episodes=1), trace_cap=700)),
+        ("nes_cartpole", lambda: gen_nes(21)),
+    ]
+    want = sys.argv[1:]
+    for name, fn in jobs:
+        if not want or any(w in name for w in want):
+            fn()
     print("golden fixtures written to", GOLDEN)
 
 

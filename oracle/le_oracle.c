@@ -500,11 +500,19 @@ static void lane_test(lane_t* L, double* rewards_out) {
         double st[4]; real_reset(c->real_env, w, st);
         float obs[LE_ORACLE_MAX_SD]; le_oracle_real_obs(c->real_env, st, obs);
         int elapsed = 0; float ep_rew = 0.f;
-        for (int t = 0; t < c->max_steps; ++t) {
+        const int K = c->same_action_num > 1 ? c->same_action_num : 1;
+        for (int t = 0; t < c->max_steps; t += K) {          /* agents/base_agent.py:193 */
             float q[LE_ORACLE_MAX_AD]; int a;
             le_oracle_q_forward(c, L->th, obs, q, &a);     /* select_test_action agents/DDQN.py:106-110 */
-            float r, d;
-            le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, obs, &r, &d);
+            float r = 0.f, d = 0.f;
+            double rsum = 0.0;                               /* EnvWrapper.step real branch envs/env_wrapper.py:56-61 */
+            for (int k = 0; k < K; ++k) {
+                float rk;
+                le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, obs, &rk, &d);
+                rsum += (double)rk;
+                if (d > 0.5f) break;
+            }
+            r = (float)rsum;
             ep_rew += r; L->test_steps++;
             if (d > 0.5f) break;
         }
@@ -549,7 +557,8 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
         float state[LE_ORACLE_MAX_SD]; le_oracle_real_obs(c->real_env, st, state);
         int elapsed = 0;
         float ep_rew = 0.f; int ep_len = 0;
-        for (int t = 0; t < c->max_steps; ++t) {
+        const int K = c->same_action_num > 1 ? c->same_action_num : 1;
+        for (int t = 0; t < c->max_steps; t += K) {          /* agents/base_agent.py:104 */
             /* select_train_action (agents/DDQN.py:97-104) */
             le_oracle_philox((uint32_t)L.train_steps, 0, LE_P_ACT, 0, k0, k1, w);
             double u = (double)(w[0] >> 8) * (1.0 / 16777216.0);
@@ -557,16 +566,33 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
             if (explore) a = (int)mulhi32(w[1], (uint32_t)ad);
             else { float q[LE_ORACLE_MAX_AD]; le_oracle_q_forward(c, L.th, state, q, &a); }
             /* env.step */
-            float ns[LE_ORACLE_MAX_SD], r, d;
+            float ns[LE_ORACLE_MAX_SD], r = 0.f, d = 0.f;
             if (c->env_kind == LE_ENV_SE) {
-                le_oracle_se_step(c, env_theta, state, a, ns, &r, &d);
+                /* EnvWrapper.step virtual branch (envs/env_wrapper.py:24-30): same_action_num chained SE steps, fp32 reward sum,
+                 * no break on done; done of the last step */
+                float cur[LE_ORACLE_MAX_SD]; memcpy(cur, state, sizeof(float) * sd);
+                for (int k = 0; k < K; ++k) {
+                    float rk;
+                    le_oracle_se_step(c, env_theta, cur, a, ns, &rk, &d);
+                    r = k == 0 ? rk : r + rk;
+                    memcpy(cur, ns, sizeof(float) * sd);
+                }
             } else {
-                float rr;
-                le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, ns, &rr, &d);
-                if (c->env_kind == LE_ENV_RN) {
-                    /* RewardEnv.step: state/next_state are the fp64 gym states cast to f32 (:78-79) */
-                    if (le_oracle_rn_reward(c, env_theta, state, ns, rr, &r) != 0) { free(L.th); free(L.rb); free(batch); free(test_tmp); return -2; }
-                } else r = rr;
+                /* real branch (envs/env_wrapper.py:56-61): python-float reward sum, break on done */
+                float cur[LE_ORACLE_MAX_SD]; memcpy(cur, state, sizeof(float) * sd);
+                double rsum = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    float rr, rk;
+                    le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, ns, &rr, &d);
+                    if (c->env_kind == LE_ENV_RN) {
+                        /* RewardEnv.step: state/next_state are the fp64 gym states cast to f32 (:78-79) */
+                        if (le_oracle_rn_reward(c, env_theta, cur, ns, rr, &rk) != 0) { free(L.th); free(L.rb); free(batch); free(test_tmp); return -2; }
+                    } else rk = rr;
+                    rsum += (double)rk;
+                    memcpy(cur, ns, sizeof(float) * sd);
+                    if (d > 0.5f) break;
+                }
+                r = (float)rsum;
             }
             /* replay_buffer.add (utils.py:24-32) */
             float* row = L.rb + (size_t)L.rb_ptr * ROW;
@@ -575,7 +601,7 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
             L.rb_ptr = (L.rb_ptr + 1) % L.rb_cap;
             L.rb_size = L.rb_size + 1 < L.rb_cap ? L.rb_size + 1 : L.rb_cap;
             memcpy(state, ns, sizeof(float) * sd);
-            ep_rew += r; ep_len += 1;
+            ep_rew += r; ep_len += K;                      /* episode_length += same_action_num :123 */
             float loss = NAN;
             if (episode >= c->init_episodes) { /* learn (agents/DDQN.py:60-95) */
                 for (int b = 0; b < c->batch_size; b += 4) {

@@ -140,7 +140,8 @@ def _run_fused(ops, cfg, env_theta, keys, q_init, trace_cap=0, n_env=1, env_inde
     return bufs
 
 
-@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling"])
+@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling", "cartpole_se_k2",
+                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real"])
 def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
     """The fused persistent kernel, one lane, against the reference's own BaseAgent.train trace."""
     g = load_golden("trajectory_%s.npz" % tag)
@@ -303,6 +304,8 @@ def _edge_cfg(**over):
     ("no_test_env", dict(use_test_env=0, early_out_num=1)),   # virtual-env plateau early-out rule
     ("init_only", dict(init_episodes=9)),                     # never learns: pure acting / replay filling
     ("solved_early_out", dict(solved_reward=5.0)),            # real-env early-out fires after the first learning episode
+    ("same_action_3", dict(same_action_num=3)),               # EnvWrapper.step repeats the action (SE: chained steps, summed reward)
+    ("same_action_odd", dict(same_action_num=7, max_steps=200)),   # max_steps not a multiple of same_action_num
 ])
 def test_fused_edge_cases_vs_oracle(ops, name, over):
     cfg, theta = _edge_cfg(**over)
@@ -328,7 +331,7 @@ def test_fused_edge_cases_vs_oracle(ops, name, over):
 def test_general_kernel_edge_cases_vs_oracle(ops):
     g = load_golden("trajectory_cartpole_se_dueling.npz")
     for over in (dict(rb_size=41, batch_size=70), dict(test_episodes=70, train_episodes=2), dict(step_budget=120),
-                 dict(q_kind=0, q_layers=2, q_hidden=150, q_feature_dim=0, q_act=1)):
+                 dict(q_kind=0, q_layers=2, q_hidden=150, q_feature_dim=0, q_act=1), dict(same_action_num=2)):
         cfg = cfg_from_bytes(g["cfg"])
         cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 3, 2, 1
         for k, v in over.items():

@@ -76,7 +76,8 @@ def test_real_env_dynamics(tag, stepfn):
             assert r == np.float32(g["ep%d_rewards" % ep][t]) and bool(d) == bool(g["ep%d_dones" % ep][t])
 
 
-@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling"])
+@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling", "cartpole_se_k2",
+                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real"])
 def test_trajectory_lockstep(tag):
     g = load_golden("trajectory_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
