@@ -15,7 +15,7 @@ import torch
 
 from . import config as le_config
 from . import ops
-from ._abi import ENV_SE, LaneCfg
+from ._abi import ENV_REAL, ENV_SE, LaneCfg
 from .agents import vary_hyperparameters
 from .rng import lane_keys
 
@@ -51,15 +51,32 @@ def _max_cfg(cfgs):
     return m
 
 
-def train_test_agents(config, se_theta, agents_num=10, seed=0, overrides=None, vary=True, env_slopes=None, device="cuda"):
-    """Returns (reward_list [agents][test_episodes], train_steps_needed [agents], episodes_needed [agents], lane_cfgs)."""
+def evaluate_agents(config, env_thetas, agents_num=10, seed=0, overrides=None, vary=True, env_slopes=None, device="cuda",
+                    env_kind=ENV_SE, n_envs=None):
+    """`agents_num` freshly sampled agents on EACH of the given training environments, all lanes in one launch per
+    kernel family (lane = env * agents_num + agent; lanes of one environment share its weight pack).
+
+    env_thetas: [n_env, P] SE parameter vectors (ENV_SE), or None with env_kind=ENV_REAL and n_envs repetitions
+    (mode 0 of experiments/syn_env_run_vary_hp.py:48-59: train on the real env itself).
+    Returns (rewards [n_env][agents][test_episodes], train_steps [n_env][agents], episodes [n_env][agents], lane_cfgs)."""
+    if env_thetas is None:
+        n_env = int(n_envs or 1)
+        theta = None
+    else:
+        theta = torch.as_tensor(np.asarray(env_thetas, np.float32)).to(device)
+        theta = theta.reshape(1, -1) if theta.dim() == 1 else theta
+        theta = theta.contiguous()
+        n_env = theta.shape[0]
+    n = n_env * agents_num
     rng = np.random.RandomState(seed)
-    cfgs = sample_agent_cfgs(config, agents_num, rng, overrides, vary, env_slopes)
-    keys = lane_keys(seed, 0, np.arange(agents_num), np.zeros(agents_num, int), np.zeros(agents_num, int))
-    theta = torch.as_tensor(np.asarray(se_theta, np.float32)).to(device).reshape(1, -1).contiguous()
-    rewards = [None] * agents_num
-    steps = [0] * agents_num
-    episodes = [0] * agents_num
+    cfgs = sample_agent_cfgs(config, n, rng, overrides, vary, env_slopes)
+    for c in cfgs:
+        c.env_kind = env_kind
+    env_of = np.arange(n) // agents_num
+    keys = lane_keys(seed, 0, env_of, np.zeros(n, int), np.arange(n) % agents_num)
+    rewards = [None] * n
+    steps = [0] * n
+    episodes = [0] * n
     groups = {True: [], False: []}
     for i, c in enumerate(cfgs):
         groups[c.q_is_register_resident()].append(i)
@@ -68,13 +85,122 @@ def train_test_agents(config, se_theta, agents_num=10, seed=0, overrides=None, v
             continue
         sub = [cfgs[i] for i in idx]
         cfg0 = _max_cfg(sub)
-        bufs = ops.InnerLoopBuffers(cfg0, len(idx), 1, device, n_cfg=len(idx))
-        ops.inner_loop_run(bufs, sub, theta, None, ops.keys_tensor(keys[idx], device), cfg0=cfg0)
+        bufs = ops.InnerLoopBuffers(cfg0, len(idx), max(n_env, 1), device, n_cfg=len(idx))
+        env_index = None if theta is None or n_env == 1 else torch.as_tensor(env_of[idx].astype(np.int32)).to(device)
+        ops.inner_loop_run(bufs, sub, theta, env_index, ops.keys_tensor(keys[idx], device), cfg0=cfg0)
         torch.cuda.current_stream().synchronize()
         out = bufs.results()
         tr = bufs.test_rewards.cpu().numpy()
         for k, i in enumerate(idx):
             rewards[i] = tr[k, :cfgs[i].test_episodes].tolist()
-            steps[i] = int(out["train_steps"][k])
+            steps[i] = int(out["train_steps"][k]) * max(int(cfgs[i].same_action_num), 1)   # sum(episode_length)
             episodes[i] = int(out["n_episodes"][k])
-    return rewards, steps, episodes, cfgs
+    nest = lambda v: [v[e * agents_num:(e + 1) * agents_num] for e in range(n_env)]
+    return nest(rewards), nest(steps), nest(episodes), cfgs
+
+
+def train_test_agents(config, se_theta, agents_num=10, seed=0, overrides=None, vary=True, env_slopes=None, device="cuda"):
+    """One SE: returns (reward_list [agents][test_episodes], train_steps_needed [agents], episodes_needed [agents], lane_cfgs)."""
+    r, s, e, cfgs = evaluate_agents(config, np.asarray(se_theta, np.float32).reshape(1, -1), agents_num, seed, overrides, vary,
+                                    env_slopes, device)
+    return r[0], s[0], e[0], cfgs
+
+
+def train_test_agents_envs(train_env, test_env, config, agents_num, seed=0, overrides=None, vary=None):
+    """Drop-in for the evaluator callback `custom_train_test_agents(train_env, test_env, config, agents_num)`
+    (experiments/syn_env_evaluate_cartpole_vary_hp_2.py:25-48): same return shape
+    (reward_list [[test rewards]...], train_steps_needed [[n]...], episodes_needed [[n]...]), all agents in one launch."""
+    kind, theta, fields = train_env.kernel_env()
+    if vary is None:
+        vary = True      # the evaluator sets config['agents']['ddqn_vary']['vary_hp'] = True (:31)
+    slopes = fields.get("env_slope")
+    if kind == ENV_SE:
+        r, s, e, _ = evaluate_agents(config, theta.numpy().reshape(1, -1), agents_num, seed, overrides, vary, slopes)
+    else:
+        if kind != ENV_REAL:
+            raise NotImplementedError("vary_hp evaluation trains on a synthetic env or on the real env")
+        r, s, e, _ = evaluate_agents(config, None, agents_num, seed, overrides, vary, None, env_kind=ENV_REAL, n_envs=1)
+    return r[0], [[x] for x in s[0]], [[x] for x in e[0]]
+
+
+def load_envs_and_config(file_name, model_dir, device):
+    """experiments/syn_env_evaluate_cartpole_vary_hp_2.py:12-22: checkpoint {'model': state_dict, 'config': config}
+    (agents/GTN_master.py:133-139) -> (virtual_env, real_env, config)."""
+    import os
+    from .envs import EnvFactory
+    save_dict = torch.load(os.path.join(model_dir, file_name), weights_only=False)
+    config = save_dict['config']
+    config['device'] = device
+    env_factory = EnvFactory(config=config)
+    virtual_env = env_factory.generate_virtual_env()
+    virtual_env.load_state_dict(save_dict['model'])
+    real_env = env_factory.generate_real_env()
+    return virtual_env, real_env, config
+
+
+def get_all_files(with_vary_hp, model_num, model_dir, custom_load_envs_and_config, env_name, device, filter_models_list=None):
+    """experiments/syn_env_run_vary_hp.py:8-29: checkpoints of `env_name` trained with/without vary_hp, in the
+    deterministic order of their random 6-character suffix."""
+    import os
+    file_list = []
+    for file_name in os.listdir(model_dir):
+        if env_name not in file_name:
+            continue
+        _, _, config = custom_load_envs_and_config(file_name=file_name, model_dir=model_dir, device=device)
+        if config['agents']['ddqn_vary']['vary_hp'] == with_vary_hp:
+            file_list.append(file_name)
+    file_list = sorted(file_list, key=lambda elem: elem[-9:])
+    if len(file_list) < model_num and filter_models_list is None:
+        raise ValueError("Not enough saved models")
+    if filter_models_list is not None:
+        return [f for f in file_list if f in filter_models_list]
+    return file_list[:model_num]
+
+
+def run_vary_hp(mode, experiment_name, model_num, agents_num, model_dir, custom_load_envs_and_config=load_envs_and_config,
+                custom_train_test_agents=None, env_name="CartPole", pool=None, device="cuda", filter_models_list=None,
+                correlation_exp=False, out_dir=None, seed=0, overrides=None):
+    """experiments/syn_env_run_vary_hp.py:32-137 with the same modes, result lists and result file
+    (utils.save_lists): mode 0 trains on the real env, mode 1 / 2 on the SEs that were trained without / with varied
+    hyper-parameters.  `pool` is accepted and ignored: instead of one process per model, ALL models x agents are lanes
+    of one launch (custom_train_test_agents=None), or the callback is invoked per model like the reference does."""
+    from .utils import save_lists
+    if mode not in (0, 1, 2):
+        raise ValueError("mode must be 0, 1 or 2")
+    train_on_venv = mode != 0
+    with_vary_hp = mode == 2
+    env_reward_overview, reward_list, train_steps_needed, episode_length_needed = {}, [], [], []
+    import os
+    if not train_on_venv:
+        file_name = sorted(os.listdir(model_dir))[0]
+        _, real_env, config = custom_load_envs_and_config(file_name=file_name, model_dir=model_dir, device=device)
+        names = [real_env.env.env_name + "_" + str(i) for i in range(model_num)]
+        if custom_train_test_agents is None:
+            r, s, e, _ = evaluate_agents(config, None, agents_num, seed, overrides, True, None, device, env_kind=ENV_REAL, n_envs=model_num)
+            per_model = [(r[i], [[x] for x in s[i]], [[x] for x in e[i]]) for i in range(model_num)]
+        else:
+            per_model = [custom_train_test_agents(train_env=real_env, test_env=real_env, config=config, agents_num=agents_num)
+                         for _ in range(model_num)]
+    else:
+        names = get_all_files(with_vary_hp=with_vary_hp, model_num=model_num, model_dir=model_dir,
+                              custom_load_envs_and_config=custom_load_envs_and_config, env_name=env_name, device=device,
+                              filter_models_list=filter_models_list)
+        loaded = [custom_load_envs_and_config(file_name=f, model_dir=model_dir, device=device) for f in names]
+        config = loaded[-1][2]
+        if custom_train_test_agents is None:
+            thetas = np.stack([v.kernel_env()[1].numpy() for v, _, _ in loaded])
+            slopes = loaded[0][0].kernel_env()[2].get("env_slope")
+            r, s, e, _ = evaluate_agents(config, thetas, agents_num, seed, overrides, True, slopes, device)
+            per_model = [(r[i], [[x] for x in s[i]], [[x] for x in e[i]]) for i in range(len(names))]
+        else:
+            per_model = [custom_train_test_agents(train_env=v, test_env=r_, config=c, agents_num=agents_num) for v, r_, c in loaded]
+    for name, (r_i, s_i, e_i) in zip(names, per_model):
+        if correlation_exp and train_on_venv and pool is not None:
+            reward_list.append(r_i); train_steps_needed.append(s_i); episode_length_needed.append(e_i)
+        else:
+            reward_list += r_i; train_steps_needed += s_i; episode_length_needed += e_i
+        env_reward_overview[name] = {} if correlation_exp else np.hstack(r_i)
+    file_name = save_lists(mode=mode, config=config, reward_list=reward_list, train_steps_needed=train_steps_needed,
+                           episode_length_needed=episode_length_needed, env_reward_overview=env_reward_overview,
+                           experiment_name=experiment_name, out_dir=out_dir)
+    return file_name

@@ -1,4 +1,6 @@
 """GPU tests of the drop-in Python API (the reference's class / method surface) against the oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -237,7 +239,7 @@ def test_vary_hp_batched_agents_match_oracle_per_lane(le):
     rewards, steps, episodes, cfgs = vary_hp.train_test_agents(cfg, theta, agents_num=n, seed=3, overrides=over)
     assert len({(c.q_hidden, c.batch_size, c.q_layers) for c in cfgs}) > 6          # genuinely heterogeneous lanes
     assert {c.q_is_register_resident() for c in cfgs} == {True, False}
-    keys = lane_keys(3, 0, np.arange(n), np.zeros(n, int), np.zeros(n, int))
+    keys = lane_keys(3, 0, np.zeros(n, int), np.zeros(n, int), np.arange(n))
     ok = 0
     for i in range(n):
         want = c_oracle.run_lane(cfgs[i], theta, tuple(int(k) for k in keys[i]))
@@ -246,3 +248,43 @@ def test_vary_hp_batched_agents_match_oracle_per_lane(le):
             ok += 1
             assert episodes[i] == want["n_episodes"]
     assert ok >= 0.7 * n
+
+
+def test_run_vary_hp_all_models_in_one_launch(le, tmp_path):
+    """experiments/syn_env_run_vary_hp.py modes 0 and 2 on GTN-format checkpoints: result file keys / shapes of utils.save_lists."""
+    from learning_environments_b200 import vary_hp
+    cfg = le["cfgs"].get("cartpole_syn_env")
+    cfg["agents"]["ddqn_vary"]["vary_hp"] = True
+    model_dir = tmp_path / "GTN_models_CartPole-v0"
+    model_dir.mkdir()
+    thetas = {}
+    for i, suffix in enumerate(["ZZZAAA", "AAAZZZ", "MMMMMM"]):
+        torch.manual_seed(100 + i)
+        venv = le["envs"].EnvFactory(cfg).generate_virtual_env()
+        name = "CartPole-v0_%s.pt" % suffix
+        torch.save({"model": venv.state_dict(), "config": cfg}, str(model_dir / name))
+        thetas[name] = venv.env.theta().numpy()
+    over = dict(print_rate=10, early_out_num=2, train_episodes=4, init_episodes=1, test_episodes=3, early_out_virtual_diff=0.01)
+    f2 = vary_hp.run_vary_hp(mode=2, experiment_name="t", model_num=2, agents_num=3, model_dir=str(model_dir), env_name="CartPole",
+                             out_dir=str(tmp_path), seed=5, overrides=over)
+    d = torch.load(f2, weights_only=False)
+    assert os.path.basename(f2) == "2_t.pt"
+    assert len(d["reward_list"]) == 6 and all(len(r) == 3 for r in d["reward_list"])
+    assert len(d["train_steps_needed"]) == 6 and len(d["episode_length_needed"]) == 6
+    assert list(d["env_reward_overview"].index) == ["CartPole-v0_AAAZZZ.pt", "CartPole-v0_MMMMMM.pt"]     # sorted by suffix
+    assert d["env_reward_overview"].shape == (2, 9)
+    # per-lane check of the first model's agents against the CPU restatement
+    from learning_environments_b200.rng import lane_keys
+    rng = np.random.RandomState(5)
+    cfgs = vary_hp.sample_agent_cfgs(cfg, 6, rng, over, True, None)
+    keys = lane_keys(5, 0, np.arange(6) // 3, np.zeros(6, int), np.arange(6) % 3)
+    ok = 0
+    for i in range(6):
+        want = c_oracle.run_lane(cfgs[i], thetas[d["env_reward_overview"].index[i // 3]], tuple(int(k) for k in keys[i]))
+        ok += int(d["train_steps_needed"][i][0] == want["train_steps"] and d["episode_length_needed"][i][0] == want["n_episodes"])
+    assert ok >= 4
+    f0 = vary_hp.run_vary_hp(mode=0, experiment_name="t", model_num=2, agents_num=2, model_dir=str(model_dir), env_name="CartPole",
+                             out_dir=str(tmp_path), seed=6, overrides=over)
+    d0 = torch.load(f0, weights_only=False)
+    assert len(d0["reward_list"]) == 4 and list(d0["env_reward_overview"].index) == ["CartPole-v0_0", "CartPole-v0_1"]
+    assert all(1 <= e[0] <= 4 for e in d0["episode_length_needed"])

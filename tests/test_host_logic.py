@@ -142,6 +142,47 @@ def _small_gtn_config(workers=4, iters=2):
     return cfg
 
 
+def test_run_vary_hp_file_selection_and_result_format(tmp_path):
+    """experiments/syn_env_run_vary_hp.py: checkpoint filtering by vary_hp flag, suffix ordering, save_lists result dict
+    (per-model callback path; the one-launch path is covered on the GPU)."""
+    import torch
+    from learning_environments_b200 import vary_hp
+    model_dir = tmp_path / "models"
+    model_dir.mkdir()
+    for i, (suffix, flag, env) in enumerate([("ZZZAAA", True, "CartPole-v0"), ("AAAZZZ", True, "CartPole-v0"), ("BBBBBB", False, "CartPole-v0"),
+                                             ("CCCCCC", True, "Acrobot-v1")]):
+        cfg = default_configs.get("cartpole_syn_env" if env == "CartPole-v0" else "acrobot_syn_env")
+        cfg["agents"]["ddqn_vary"]["vary_hp"] = flag
+        torch.manual_seed(i)
+        venv = envs.EnvFactory(cfg).generate_virtual_env()
+        torch.save({"model": venv.state_dict(), "config": cfg}, str(model_dir / ("%s_%s.pt" % (env, suffix))))
+    calls = []
+
+    def stub(train_env, test_env, config, agents_num):
+        calls.append((train_env.is_virtual_env(), test_env.is_virtual_env(), float(train_env.env.theta().abs().sum()) if train_env.is_virtual_env() else 0.0))
+        return [[1.0, 2.0]] * agents_num, [[10]] * agents_num, [[3]] * agents_num
+
+    files = vary_hp.get_all_files(True, 2, str(model_dir), vary_hp.load_envs_and_config, "CartPole", "cpu")
+    assert files == ["CartPole-v0_AAAZZZ.pt", "CartPole-v0_ZZZAAA.pt"]
+    with pytest.raises(ValueError, match="Not enough saved models"):
+        vary_hp.get_all_files(False, 2, str(model_dir), vary_hp.load_envs_and_config, "CartPole", "cpu")
+    f = vary_hp.run_vary_hp(mode=2, experiment_name="x", model_num=2, agents_num=3, model_dir=str(model_dir),
+                            custom_train_test_agents=stub, env_name="CartPole", device="cpu", out_dir=str(tmp_path))
+    d = torch.load(f, weights_only=False)
+    assert os.path.basename(f) == "2_x.pt" and set(d) == {"config", "reward_list", "train_steps_needed", "episode_length_needed",
+                                                          "env_reward_overview"}
+    assert len(d["reward_list"]) == 6 and d["train_steps_needed"] == [[10]] * 6 and d["episode_length_needed"] == [[3]] * 6
+    assert list(d["env_reward_overview"].index) == files and d["env_reward_overview"].shape == (2, 6)
+    assert [c[:2] for c in calls] == [(True, False)] * 2 and calls[0][2] != calls[1][2]     # the two checkpoints' own weights
+    f1 = vary_hp.run_vary_hp(mode=1, experiment_name="x", model_num=1, agents_num=1, model_dir=str(model_dir),
+                             custom_train_test_agents=stub, env_name="CartPole", device="cpu", out_dir=str(tmp_path))
+    assert list(torch.load(f1, weights_only=False)["env_reward_overview"].index) == ["CartPole-v0_BBBBBB.pt"]
+    f0 = vary_hp.run_vary_hp(mode=0, experiment_name="x", model_num=2, agents_num=1, model_dir=str(model_dir),
+                             custom_train_test_agents=stub, env_name="CartPole", device="cpu", out_dir=str(tmp_path))
+    d0 = torch.load(f0, weights_only=False)
+    assert len(d0["reward_list"]) == 2 and calls[-1][:2] == (False, False)
+
+
 def test_gtn_master_generation_logic_with_oracle_backend(monkeypatch, tmp_path):
     from oracle import nes as onese
     patch_master_for_cpu(monkeypatch)
