@@ -15,7 +15,8 @@
 namespace le {
 
 constexpr int kGThreads = 256;
-constexpr int kGTile = 64, kGChunk = 16, kGPad = 4;
+constexpr int kGTileM = 128, kGTileN = 64, kGChunk = 16, kGPad = 4;
+constexpr int kGSmemFloats = 2 * kGChunk * (kGTileM + kGPad + kGTileN + kGPad);
 
 struct GLayer { int in, out, act, w_off, b_off, y_off; };
 struct GNet {
@@ -61,61 +62,163 @@ __device__ __forceinline__ float g_act_grad(int act, float slope, float h) {
 }
 
 // C[i*c_si + j*c_sj] (+)= sum_l A[i*a_si + l*a_sl] * B[l*b_sl + j*b_sj]  (+ bias[j], activation)   — whole CTA.
-__device__ void g_gemm(const float* __restrict__ A, int a_si, int a_sl, const float* __restrict__ B, int b_sl, int b_sj,
-                       float* __restrict__ C, int c_si, int c_sj, int I, int J, int L, const float* __restrict__ bias, int act,
-                       float slope, bool accumulate, float* sm) {
-    float* As = sm;
-    float* Bs = sm + kGChunk * (kGTile + kGPad);
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    constexpr int LD = kGTile + kGPad;
-    for (int i0 = 0; i0 < I; i0 += kGTile) {
-        for (int j0 = 0; j0 < J; j0 += kGTile) {
-            float acc[4][4];
+// 128x64 output tiles, K chunks of 16, 8x4 accumulators per thread.  The (tile, chunk) sequence is flattened and
+// software-pipelined: the global loads of chunk s+1 are issued into registers before the FFMAs of chunk s and stored
+// to the other shared-memory stage afterwards (one __syncthreads per chunk; the L2 latency of the operand stream is
+// covered by 512 FFMA per thread).  Per-thread element coordinates inside a tile-chunk are loop invariants (element q
+// of a thread is its first element plus q constant steps), so a chunk costs one base address per operand.  Warps whose
+// 16 rows lie outside I skip the arithmetic.  The k-summation order per output element is ascending for every shape.
+__device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a_sl, const float* __restrict__ B, int b_sl, int b_sj,
+                                    float* __restrict__ C, int c_si, int c_sj, int I, int J, int L, const float* __restrict__ bias,
+                                    int act, float slope, bool accumulate, float* sm) {
+    constexpr int TM = kGTileM, TN = kGTileN, TK = kGChunk, LDA = TM + kGPad, LDB = TN + kGPad;
+    constexpr int NA = TM * TK / kGThreads, NB = TN * TK / kGThreads;   // 8, 4 prefetch registers
+    float* As = sm;                       // [2][TK][LDA]
+    float* Bs = sm + 2 * TK * LDA;        // [2][TK][LDB]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, warp = tid >> 5;
+    const int n_jt = (J + TN - 1) / TN, n_lc = (L + TK - 1) / TK;
+    const int total = ((I + TM - 1) / TM) * n_jt * n_lc;
+    const bool akm = a_sl == 1, bkm = b_sl == 1;   // operand stored k-major (k contiguous) or not
+    // element q of this thread inside a tile-chunk: A (ia + q*dia, la + q*dla), B (lb + q*dlb, jb + q*djb)
+    const int ia = akm ? (tid >> 4) : (tid & (TM - 1)), la = akm ? (tid & (TK - 1)) : (tid / TM);
+    const int dia = akm ? kGThreads / TK : 0, dla = akm ? 0 : kGThreads / TM;
+    const int jb = bkm ? (tid >> 4) : (tid & (TN - 1)), lb = bkm ? (tid & (TK - 1)) : (tid / TN);
+    const int djb = bkm ? kGThreads / TK : 0, dlb = bkm ? 0 : kGThreads / TN;
+    const int64_t gdA = (int64_t)dia * a_si + (int64_t)dla * a_sl, gdB = (int64_t)dlb * b_sl + (int64_t)djb * b_sj;
+    const int sA0 = la * LDA + ia, sdA = dla * LDA + dia, sB0 = lb * LDB + jb, sdB = dlb * LDB + djb;
+    float pa[NA], pb[NB];
+    auto fetch = [&](int i0, int j0, int l0) {
+        const float* a = A + (int64_t)(i0 + ia) * a_si + (int64_t)(l0 + la) * a_sl;
+        const float* b = B + (int64_t)(l0 + lb) * b_sl + (int64_t)(j0 + jb) * b_sj;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+        for (int q = 0; q < NA; ++q)
+            pa[q] = (i0 + ia + q * dia < I && l0 + la + q * dla < L) ? __ldcg(a + q * gdA) : 0.f;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-            for (int l0 = 0; l0 < L; l0 += kGChunk) {
+        for (int q = 0; q < NB; ++q)
+            pb[q] = (j0 + jb + q * djb < J && l0 + lb + q * dlb < L) ? __ldcg(b + q * gdB) : 0.f;
+    };
+    auto stash = [&](int buf) {
+        float* as = As + buf * TK * LDA + sA0;
+        float* bs = Bs + buf * TK * LDB + sB0;
 #pragma unroll
-                for (int q = 0; q < (kGTile * kGChunk) / kGThreads; ++q) {
-                    const int e = tid + kGThreads * q;
-                    int l, i;
-                    if (a_sl == 1) { l = e & (kGChunk - 1); i = e >> 4; } else { i = e & (kGTile - 1); l = e >> 6; }
-                    const int gi = i0 + i, gl = l0 + l;
-                    As[l * LD + i] = (gi < I && gl < L) ? A[(int64_t)gi * a_si + (int64_t)gl * a_sl] : 0.f;
-                    int lb, j;
-                    if (b_sl == 1) { lb = e & (kGChunk - 1); j = e >> 4; } else { j = e & (kGTile - 1); lb = e >> 6; }
-                    const int gj = j0 + j, glb = l0 + lb;
-                    Bs[lb * LD + j] = (gj < J && glb < L) ? B[(int64_t)glb * b_sl + (int64_t)gj * b_sj] : 0.f;
-                }
-                __syncthreads();
+        for (int q = 0; q < NA; ++q) as[q * sdA] = pa[q];
 #pragma unroll
-                for (int l = 0; l < kGChunk; ++l) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(As + l * LD + 4 * ty);
-                    const float4 b4 = *reinterpret_cast<const float4*>(Bs + l * LD + 4 * tx);
-                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int q = 0; q < NB; ++q) bs[q * sdB] = pb[q];
+    };
+    float acc[8][4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
-                }
-                __syncthreads();
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    fetch(0, 0, 0);
+    stash(0);
+    __syncthreads();
+    int it = 0, jt = 0, lc = 0;   // current (tile row, tile column, chunk)
+    for (int s = 0; s < total; ++s) {
+        const int buf = s & 1;
+        const int i0 = it * TM, j0 = jt * TN;
+        const bool tile_done = lc == n_lc - 1;
+        int nit = it, njt = jt, nlc = lc + 1;
+        if (tile_done) { nlc = 0; njt = jt + 1; if (njt == n_jt) { njt = 0; nit = it + 1; } }
+        if (s + 1 < total) fetch(nit * TM, njt * TN, nlc * TK);
+        if (i0 + 16 * warp < I) {
+            const float* as = As + buf * TK * LDA + 8 * ty;
+            const float* bs = Bs + buf * TK * LDB + 4 * tx;
+#pragma unroll
+            for (int l = 0; l < TK; ++l) {
+                const float4 a0 = *reinterpret_cast<const float4*>(as + l * LDA);
+                const float4 a1 = *reinterpret_cast<const float4*>(as + l * LDA + 4);
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + l * LDB);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
             }
+        }
+        if (s + 1 < total) stash(buf ^ 1);
+        if (tile_done) {   // epilogue of tile (it, jt)
+            float bj[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int i = i0 + 4 * ty + a;
+            for (int b = 0; b < 4; ++b) bj[b] = (bias && j0 + 4 * tx + b < J) ? __ldcg(bias + j0 + 4 * tx + b) : 0.f;
+            if (i0 + 16 * warp < I) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int j = j0 + 4 * tx + b;
-                    if (i < I && j < J) {
-                        float v = acc[a][b];
-                        float* dst = C + (int64_t)i * c_si + (int64_t)j * c_sj;
-                        if (accumulate) v += *dst;
-                        if (bias) v += bias[j];
-                        *dst = g_act(act, slope, v);
+                for (int a = 0; a < 8; ++a) {
+                    const int i = i0 + 8 * ty + a;
+                    float* row = C + (int64_t)i * c_si + (int64_t)(j0 + 4 * tx) * c_sj;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (i < I && j0 + 4 * tx + b < J) {
+                            float v = acc[a][b];
+                            if (accumulate) v += __ldcg(row + b * c_sj);
+                            if (bias) v += bj[b];
+                            __stcg(row + b * c_sj, g_act(act, slope, v));
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        }
+        it = nit; jt = njt; lc = nlc;
+        __syncthreads();
+    }
+}
+
+// Dense layer forward for M <= MT rows (greedy action M = 1, batched test rollouts M <= 16): thread j owns output
+// column j and streams its weight row W[j][:] (16-byte loads when the rows are aligned); the input rows sit in shared
+// memory as Xs[k][m] and are read as broadcasts.  Same ascending-k fmaf chain per output as g_gemm.
+template <int MT>
+__device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int M,
+                           float* __restrict__ acts, int S, float slope, float* sm) {
+    constexpr int KB = (kGSmemFloats / MT) / 4 * 4 > 512 ? 512 : (kGSmemFloats / MT) / 4 * 4;
+    const int tid = threadIdx.x;
+    for (int o0 = 0; o0 < l.out; o0 += kGThreads) {
+        const int j = o0 + tid;
+        float acc[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+        for (int k0 = 0; k0 < l.in; k0 += KB) {
+            const int kn = min(KB, l.in - k0);
+            __syncthreads();
+            for (int e = tid; e < kn * MT; e += kGThreads) {
+                const int k = e / MT, m = e % MT;
+                sm[e] = m < M ? __ldcg(X + (int64_t)m * xs + k0 + k) : 0.f;
+            }
+            __syncthreads();
+            if (j < l.out) {
+                const float* wr = th + l.w_off + (int64_t)j * l.in + k0;
+                const bool vec = ((l.in | kn) & 3) == 0 && (reinterpret_cast<uintptr_t>(wr) & 15) == 0;
+                auto mac = [&](int k, float w) {
+                    if constexpr (MT == 1) acc[0] = fmaf(sm[k], w, acc[0]);
+                    else {
+#pragma unroll
+                        for (int m4 = 0; m4 < MT / 4; ++m4) {
+                            const float4 x = *reinterpret_cast<const float4*>(sm + k * MT + 4 * m4);
+                            acc[4 * m4] = fmaf(x.x, w, acc[4 * m4]); acc[4 * m4 + 1] = fmaf(x.y, w, acc[4 * m4 + 1]);
+                            acc[4 * m4 + 2] = fmaf(x.z, w, acc[4 * m4 + 2]); acc[4 * m4 + 3] = fmaf(x.w, w, acc[4 * m4 + 3]);
+                        }
+                    }
+                };
+                if (vec) {
+#pragma unroll 4
+                    for (int k = 0; k < kn; k += 4) {
+                        const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wr + k));
+                        mac(k, w4.x); mac(k + 1, w4.y); mac(k + 2, w4.z); mac(k + 3, w4.w);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int k = 0; k < kn; ++k) mac(k, __ldcg(wr + k));
+                }
+            }
+        }
+        if (j < l.out) {
+            const float bj = __ldcg(th + l.b_off + j);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                if (m < M) __stcg(acts + (int64_t)m * S + l.y_off + j, g_act(l.act, slope, acc[m] + bj));
         }
     }
     __syncthreads();
@@ -123,6 +226,8 @@ __device__ void g_gemm(const float* __restrict__ A, int a_si, int a_sl, const fl
 
 __device__ __forceinline__ void g_layer_fwd(const GLayer& l, const float* th, const float* X, int xs, int B, float* acts, int S,
                                             float slope, float* sm) {
+    if (B == 1) { g_thin_fwd<1>(l, th, X, xs, B, acts, S, slope, sm); return; }
+    if (B <= 16) { g_thin_fwd<16>(l, th, X, xs, B, acts, S, slope, sm); return; }
     g_gemm(X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, sm);
 }
 
@@ -180,15 +285,42 @@ __device__ void g_q_values(const GNet& n, const float* acts, int B, float* q, fl
 // dX (may be null) receives / accumulates dL/dX with row stride dxs.
 __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const float* X, int xs, const float* acts, float* dact,
                             int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm) {
-    for (int e = threadIdx.x; e < B * l.out; e += kGThreads) {
-        const int64_t o = (int64_t)(e / l.out) * S + l.y_off + (e % l.out);
-        dact[o] *= g_act_grad(l.act, slope, acts[o]);
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < l.out; o += kGThreads) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += dact[(int64_t)b * S + l.y_off + o];
-        grad[l.b_off + o] = s;
+    // dZ = dY * act'(Y) in place, and db[o] = sum_b dZ[b][o]: thread (rg, o) walks rows rg, rg+RG, ... of column o
+    // (coalesced across o, independent loads down the column), partial sums meet in shared memory in fixed order.
+    for (int o0 = 0; o0 < l.out; o0 += kGThreads) {
+        const int cw = min(l.out - o0, kGThreads), RG = kGThreads / cw;
+        const int rg = threadIdx.x / cw, o = o0 + threadIdx.x % cw;
+        float part = 0.f;
+        if (rg < RG) {
+            constexpr int UN = 8;   // rows in flight per thread: the loop is L2-latency bound, not bandwidth bound
+            for (int b = rg; b < B; b += UN * RG) {
+                float dy[UN], y[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int bb = b + u * RG;
+                    const int64_t at = (int64_t)(bb < B ? bb : b) * S + l.y_off + o;
+                    dy[u] = __ldcg(dact + at);
+                    y[u] = __ldcg(acts + at);
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int bb = b + u * RG;
+                    if (bb < B) {
+                        const float dz = dy[u] * g_act_grad(l.act, slope, y[u]);
+                        __stcg(dact + (int64_t)bb * S + l.y_off + o, dz);
+                        part += dz;
+                    }
+                }
+            }
+            sm[rg * cw + (o - o0)] = part;
+        }
+        __syncthreads();
+        if (threadIdx.x < cw) {
+            float t = 0.f;
+            for (int r = 0; r < RG; ++r) t += sm[r * cw + threadIdx.x];
+            grad[l.b_off + o0 + threadIdx.x] = t;
+        }
+        __syncthreads();
     }
     // dW[o][i] = sum_b dZ[b][o] * X[b][i]
     g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
@@ -262,27 +394,41 @@ __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars&
     const double bc1 = 1.0 - ls.b1pow, bc2 = 1.0 - ls.b2pow;
     const float neg_step = (float)(-(ls.lr / bc1));
     const float bc2s = (float)sqrt(bc2);
-    for (int p = threadIdx.x; p < n.P; p += kGThreads) {
-        const float g = w.grad[p];
-        float m = w.m[p], v = w.v[p];
-        m = m + ls.w1 * (g - m);
-        v = v * ls.beta2;
-        v = v + (ls.w2 * g) * g;
-        w.m[p] = m;
-        w.v[p] = v;
-        const float denom = __fdiv_rn(__fsqrt_rn(v), bc2s) + ls.eps;
-        const float pn = w.theta[p] + __fdiv_rn(neg_step * m, denom);
-        w.theta[p] = pn;
-        w.thetaT[p] = ls.tau * pn + ls.one_minus_tau * w.thetaT[p];
+    {
+        constexpr int UN = 4;   // parameters in flight per thread (5 loads each)
+        for (int p0 = threadIdx.x; p0 < n.P; p0 += UN * kGThreads) {
+            float g[UN], m[UN], v[UN], th[UN], tt[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int p = p0 + u * kGThreads < n.P ? p0 + u * kGThreads : p0;
+                g[u] = __ldcg(w.grad + p); m[u] = __ldcg(w.m + p); v[u] = __ldcg(w.v + p);
+                th[u] = __ldcg(w.theta + p); tt[u] = __ldcg(w.thetaT + p);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int p = p0 + u * kGThreads;
+                if (p < n.P) {
+                    float mm = m[u] + ls.w1 * (g[u] - m[u]);
+                    float vv = v[u] * ls.beta2;
+                    vv = vv + (ls.w2 * g[u]) * g[u];
+                    __stcg(w.m + p, mm);
+                    __stcg(w.v + p, vv);
+                    const float denom = __fdiv_rn(__fsqrt_rn(vv), bc2s) + ls.eps;
+                    const float pn = th[u] + __fdiv_rn(neg_step * mm, denom);
+                    __stcg(w.theta + p, pn);
+                    __stcg(w.thetaT + p, ls.tau * pn + ls.one_minus_tau * tt[u]);
+                }
+            }
+        }
     }
     __syncthreads();
     return loss;
 }
 
 // greedy action of ONE state row (select_train/test_action); result uniform across the CTA
-__device__ int g_greedy_row(const GNet& n, const GSlot& w, const float* state_sm /* [sd] in shared memory */, float* sm, float* red,
+__device__ int g_greedy_row(const GNet& n, const GSlot& w, const float* state_row /* [sd] in global memory */, float* sm, float* red,
                             int* ibox) {
-    g_net_forward(n, w.theta, state_sm, n.sd, 1, w.actB, sm);
+    g_net_forward(n, w.theta, state_row, n.sd, 1, w.actB, sm);
     g_q_values(n, w.actB, 1, w.q2, red);
     if (threadIdx.x == 0) {
         int best = 0;
@@ -340,9 +486,9 @@ __device__ void g_init_layer(const GLayer& l, float* th, uint32_t k0, uint32_t k
 }
 
 template <int SD, int AD>
-__global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParams G) {
+__global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunParams G) {
     using RL = RowLayout<SD>;
-    __shared__ __align__(16) float sm[2 * kGChunk * (kGTile + kGPad)];
+    __shared__ __align__(16) float sm[kGSmemFloats];
     __shared__ float red[32];
     __shared__ __align__(16) float box[16];   // state row / env step results broadcast
     __shared__ int ibox[4];
@@ -476,9 +622,9 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
                 if (explore) action = (int)__umulhi(wa.y, (uint32_t)AD);
                 else {
                     __syncthreads();
-                    if (tid < SD) box[tid] = state[tid];
+                    if (tid < SD) __stcg(w.xs + tid, state[tid]);   // operand rows are read with ld.global.cg: stage in the slot
                     __syncthreads();
-                    action = g_greedy_row(n, w, box, sm, red, ibox);
+                    action = g_greedy_row(n, w, w.xs, sm, red, ibox);
                 }
                 float ns[SD], r = 0.f, d = 0.f;
                 if (c.env_kind == LE_ENV_SE) {
@@ -612,11 +758,11 @@ __global__ void __launch_bounds__(kGThreads) general_loop_kernel(const GRunParam
 
 // unit kernels on caller-owned canonical arrays (same layout as the slot's theta/thetaT/m/v)
 template <int SD, int AD>
-__global__ void __launch_bounds__(kGThreads)
+__global__ void __launch_bounds__(kGThreads, 2)
 general_td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, GNet n, float* th, float* thT, float* m, float* v, int32_t* tcount,
                          int q_stride, const float* __restrict__ rows, int B, float* __restrict__ loss_out, float* scratch,
                          int64_t scratch_stride) {
-    __shared__ __align__(16) float sm[2 * kGChunk * (kGTile + kGPad)];
+    __shared__ __align__(16) float sm[kGSmemFloats];
     __shared__ float red[32];
     const int id = blockIdx.x, tid = threadIdx.x;
     const le_lane_cfg c = *cfg_dev;
@@ -653,7 +799,7 @@ template <int SD, int AD>
 __global__ void __launch_bounds__(kGThreads)
 general_qnet_forward_kernel(GNet n, const float* __restrict__ q_theta, int q_stride, const float* __restrict__ state,
                             float* __restrict__ q_out, int32_t* __restrict__ argmax, float* scratch, int64_t scratch_stride) {
-    __shared__ __align__(16) float sm[2 * kGChunk * (kGTile + kGPad)];
+    __shared__ __align__(16) float sm[kGSmemFloats];
     __shared__ float red[32];
     const int id = blockIdx.x;
     float* acts = scratch + (int64_t)id * scratch_stride;
