@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--workload", default="cartpole_se", choices=sorted(WORKLOADS))
     ap.add_argument("--members-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lane-override", action="append", default=[], metavar="FIELD=VALUE",
+                    help="profiling aid: override an le_lane_cfg field (e.g. max_steps=100); recorded in config.overrides")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -233,6 +235,9 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     d, cfg = build_lane_cfg(args.workload)
+    for ov in args.lane_override:
+        k, v = ov.split("=")
+        setattr(cfg, k, type(getattr(cfg, k))(float(v)))
     gtn = d["agents"]["gtn"]
     mpg = args.members_per_gpu or WORKLOADS[args.workload]["members_per_gpu"]
     pop = mpg * world
@@ -356,7 +361,7 @@ def main():
             "metric": "se_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, cfg, mpg, plan),
+            "config": dict(workload_config(args.workload, cfg, mpg, plan), **({"overrides": args.lane_override} if args.lane_override else {})),
             "nes_generations_per_hour": 3600.0 / (e2e_s / max(args.steps, 1)), "nes_population": pop,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": ev.h2d_bytes, "d2h_bytes_per_step": ev.d2h_bytes},
             "gpu_launches": 3 * args.steps,

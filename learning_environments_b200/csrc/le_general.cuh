@@ -50,6 +50,11 @@ __host__ __device__ inline void gnet_build(const le_lane_cfg* c, GNet* n) {
     n->P = p; n->sum_out = y;
 }
 
+// 4-byte asynchronous global -> shared copy; !valid copies nothing and writes zero (src-size 0)
+__device__ __forceinline__ void cp_async4_zfill(uint32_t saddr, const void* gptr, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(gptr), "r"(valid ? 4 : 0) : "memory");
+}
+
 __device__ __forceinline__ float g_act(int act, float slope, float z) {
     if (act == 1) return tanh_one(z);
     if (act == 2) return fmaxf(z, slope * z);
@@ -63,8 +68,8 @@ __device__ __forceinline__ float g_act_grad(int act, float slope, float h) {
 
 // C[i*c_si + j*c_sj] (+)= sum_l A[i*a_si + l*a_sl] * B[l*b_sl + j*b_sj]  (+ bias[j], activation)   — whole CTA.
 // 128x64 output tiles, K chunks of 16, 8x4 accumulators per thread.  The (tile, chunk) sequence is flattened and
-// software-pipelined: the global loads of chunk s+1 are issued into registers before the FFMAs of chunk s and stored
-// to the other shared-memory stage afterwards (one __syncthreads per chunk; the L2 latency of the operand stream is
+// software-pipelined over two shared-memory stages: the operands of chunk s+1 travel global -> shared with cp.async
+// while the FFMAs of chunk s run (one wait + one __syncthreads per chunk; the L2 latency of the operand stream is
 // covered by 512 FFMA per thread).  Per-thread element coordinates inside a tile-chunk are loop invariants (element q
 // of a thread is its first element plus q constant steps), so a chunk costs one base address per operand.  Warps whose
 // 16 rows lie outside I skip the arithmetic.  The k-summation order per output element is ascending for every shape.
@@ -72,7 +77,7 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
                                     float* __restrict__ C, int c_si, int c_sj, int I, int J, int L, const float* __restrict__ bias,
                                     int act, float slope, bool accumulate, float* sm) {
     constexpr int TM = kGTileM, TN = kGTileN, TK = kGChunk, LDA = TM + kGPad, LDB = TN + kGPad;
-    constexpr int NA = TM * TK / kGThreads, NB = TN * TK / kGThreads;   // 8, 4 prefetch registers
+    constexpr int NA = TM * TK / kGThreads, NB = TN * TK / kGThreads;   // 8 + 4 elements per thread per chunk
     float* As = sm;                       // [2][TK][LDA]
     float* Bs = sm + 2 * TK * LDA;        // [2][TK][LDB]
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, warp = tid >> 5;
@@ -86,32 +91,33 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
     const int djb = bkm ? kGThreads / TK : 0, dlb = bkm ? 0 : kGThreads / TN;
     const int64_t gdA = (int64_t)dia * a_si + (int64_t)dla * a_sl, gdB = (int64_t)dlb * b_sl + (int64_t)djb * b_sj;
     const int sA0 = la * LDA + ia, sdA = dla * LDA + dia, sB0 = lb * LDB + jb, sdB = dlb * LDB + djb;
-    float pa[NA], pb[NB];
-    auto fetch = [&](int i0, int j0, int l0) {
+    // operand stream: 4-byte cp.async straight into the shared-memory stage (any stride, transposing on the fly,
+    // out-of-range elements zero-filled through src-size 0) — no staging registers, nothing for the compiler to spill
+    const uint32_t sm_u32 = (uint32_t)__cvta_generic_to_shared(sm);
+    auto issue = [&](int buf, int i0, int j0, int l0) {
         const float* a = A + (int64_t)(i0 + ia) * a_si + (int64_t)(l0 + la) * a_sl;
         const float* b = B + (int64_t)(l0 + lb) * b_sl + (int64_t)(j0 + jb) * b_sj;
+        const uint32_t sa = sm_u32 + 4u * (uint32_t)(buf * TK * LDA + sA0);
+        const uint32_t sb = sm_u32 + 4u * (uint32_t)(2 * TK * LDA + buf * TK * LDB + sB0);
 #pragma unroll
-        for (int q = 0; q < NA; ++q)
-            pa[q] = (i0 + ia + q * dia < I && l0 + la + q * dla < L) ? __ldcg(a + q * gdA) : 0.f;
+        for (int q = 0; q < NA; ++q) {
+            const bool ok = i0 + ia + q * dia < I && l0 + la + q * dla < L;
+            cp_async4_zfill(sa + 4u * (uint32_t)(q * sdA), ok ? a + q * gdA : A, ok);
+        }
 #pragma unroll
-        for (int q = 0; q < NB; ++q)
-            pb[q] = (j0 + jb + q * djb < J && l0 + lb + q * dlb < L) ? __ldcg(b + q * gdB) : 0.f;
-    };
-    auto stash = [&](int buf) {
-        float* as = As + buf * TK * LDA + sA0;
-        float* bs = Bs + buf * TK * LDB + sB0;
-#pragma unroll
-        for (int q = 0; q < NA; ++q) as[q * sdA] = pa[q];
-#pragma unroll
-        for (int q = 0; q < NB; ++q) bs[q * sdB] = pb[q];
+        for (int q = 0; q < NB; ++q) {
+            const bool ok = j0 + jb + q * djb < J && l0 + lb + q * dlb < L;
+            cp_async4_zfill(sb + 4u * (uint32_t)(q * sdB), ok ? b + q * gdB : B, ok);
+        }
+        cp_async_commit();
     };
     float acc[8][4];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    fetch(0, 0, 0);
-    stash(0);
+    issue(0, 0, 0, 0);
+    cp_async_wait<0>();
     __syncthreads();
     int it = 0, jt = 0, lc = 0;   // current (tile row, tile column, chunk)
     for (int s = 0; s < total; ++s) {
@@ -120,7 +126,7 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
         const bool tile_done = lc == n_lc - 1;
         int nit = it, njt = jt, nlc = lc + 1;
         if (tile_done) { nlc = 0; njt = jt + 1; if (njt == n_jt) { njt = 0; nit = it + 1; } }
-        if (s + 1 < total) fetch(nit * TM, njt * TN, nlc * TK);
+        if (s + 1 < total) issue(buf ^ 1, nit * TM, njt * TN, nlc * TK);   // stage buf^1 was last read before the previous barrier
         if (i0 + 16 * warp < I) {
             const float* as = As + buf * TK * LDA + 8 * ty;
             const float* bs = Bs + buf * TK * LDB + 4 * tx;
@@ -136,7 +142,6 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
                     for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
             }
         }
-        if (s + 1 < total) stash(buf ^ 1);
         if (tile_done) {   // epilogue of tile (it, jt)
             float bj[4];
 #pragma unroll
@@ -163,6 +168,7 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
         }
         it = nit; jt = njt; lc = nlc;
+        cp_async_wait<0>();
         __syncthreads();
     }
 }
@@ -203,7 +209,7 @@ __device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict
                     }
                 };
                 if (vec) {
-#pragma unroll 4
+#pragma unroll 8
                     for (int k = 0; k < kn; k += 4) {
                         const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wr + k));
                         mac(k, w4.x); mac(k + 1, w4.y); mac(k + 2, w4.z); mac(k + 3, w4.w);
@@ -224,10 +230,59 @@ __device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict
     __syncthreads();
 }
 
+// Dense layer forward with at most 4 output columns and many rows (dueling heads fd -> 1 / fd -> ad): thread b owns
+// batch row b and streams X[b][:] (16-byte loads when aligned); the weights sit in shared memory as Ws[k][4] and are
+// read as broadcasts.  Same ascending-k fmaf chain per output as g_gemm.
+__device__ __noinline__ void g_thinj_fwd(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int B,
+                                         float* __restrict__ acts, int S, float slope, float* sm) {
+    constexpr int KB = 1024;
+    static_assert(KB * 4 <= kGSmemFloats, "weight stage must fit the GEMM buffer");
+    const int tid = threadIdx.x;
+    for (int b0 = 0; b0 < B; b0 += kGThreads) {
+        const int b = b0 + tid;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = 0; k0 < l.in; k0 += KB) {
+            const int kn = min(KB, l.in - k0);
+            __syncthreads();
+            for (int e = tid; e < kn * 4; e += kGThreads) {
+                const int k = e >> 2, j = e & 3;
+                sm[e] = j < l.out ? __ldcg(th + l.w_off + (int64_t)j * l.in + k0 + k) : 0.f;
+            }
+            __syncthreads();
+            if (b < B) {
+                const float* xr = X + (int64_t)b * xs + k0;
+                const bool vec = ((xs | kn | k0) & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0;
+                auto mac = [&](int k, float x) {
+                    const float4 w = *reinterpret_cast<const float4*>(sm + 4 * k);
+                    acc[0] = fmaf(x, w.x, acc[0]); acc[1] = fmaf(x, w.y, acc[1]);
+                    acc[2] = fmaf(x, w.z, acc[2]); acc[3] = fmaf(x, w.w, acc[3]);
+                };
+                if (vec) {
+#pragma unroll 4
+                    for (int k = 0; k < kn; k += 4) {
+                        const float4 x4 = __ldcg(reinterpret_cast<const float4*>(xr + k));
+                        mac(k, x4.x); mac(k + 1, x4.y); mac(k + 2, x4.z); mac(k + 3, x4.w);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int k = 0; k < kn; ++k) mac(k, __ldcg(xr + k));
+                }
+            }
+        }
+        if (b < B) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < l.out) __stcg(acts + (int64_t)b * S + l.y_off + j, g_act(l.act, slope, acc[j] + __ldcg(th + l.b_off + j)));
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void g_layer_fwd(const GLayer& l, const float* th, const float* X, int xs, int B, float* acts, int S,
                                             float slope, float* sm) {
     if (B == 1) { g_thin_fwd<1>(l, th, X, xs, B, acts, S, slope, sm); return; }
     if (B <= 16) { g_thin_fwd<16>(l, th, X, xs, B, acts, S, slope, sm); return; }
+    if (l.out <= 4) { g_thinj_fwd(l, th, X, xs, B, acts, S, slope, sm); return; }
     g_gemm(X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, sm);
 }
 
@@ -322,8 +377,9 @@ __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const
         }
         __syncthreads();
     }
-    // dW[o][i] = sum_b dZ[b][o] * X[b][i]
-    g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
+    // dW[o][i] = sum_b dZ[b][o] * X[b][i]; the longer of (out, in) takes the 128-row side of the tile
+    if (l.out >= l.in) g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
+    else g_gemm(X, 1, xs, dact + l.y_off, S, 1, grad + l.w_off, 1, l.in, l.in, l.out, B, nullptr, 0, 0.f, false, sm);
     // dX[b][i] (+)= sum_o dZ[b][o] * W[o][i]
     if (dX) g_gemm(dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, sm);
 }
