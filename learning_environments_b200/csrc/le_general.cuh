@@ -130,16 +130,23 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
         if (i0 + 16 * warp < I) {
             const float* as = As + buf * TK * LDA + 8 * ty;
             const float* bs = Bs + buf * TK * LDB + 4 * tx;
+            // fragments of step l+1 are loaded before the 32 FFMAs of step l (register double buffer)
+            float4 a0 = *reinterpret_cast<const float4*>(as), a1 = *reinterpret_cast<const float4*>(as + 4);
+            float4 b4 = *reinterpret_cast<const float4*>(bs);
 #pragma unroll
             for (int l = 0; l < TK; ++l) {
-                const float4 a0 = *reinterpret_cast<const float4*>(as + l * LDA);
-                const float4 a1 = *reinterpret_cast<const float4*>(as + l * LDA + 4);
-                const float4 b4 = *reinterpret_cast<const float4*>(bs + l * LDB);
+                float4 na0 = a0, na1 = a1, nb4 = b4;
+                if (l + 1 < TK) {
+                    na0 = *reinterpret_cast<const float4*>(as + (l + 1) * LDA);
+                    na1 = *reinterpret_cast<const float4*>(as + (l + 1) * LDA + 4);
+                    nb4 = *reinterpret_cast<const float4*>(bs + (l + 1) * LDB);
+                }
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int a = 0; a < 8; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                a0 = na0; a1 = na1; b4 = nb4;
             }
         }
         if (tile_done) {   // epilogue of tile (it, jt)
@@ -147,17 +154,22 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
 #pragma unroll
             for (int b = 0; b < 4; ++b) bj[b] = (bias && j0 + 4 * tx + b < J) ? __ldcg(bias + j0 + 4 * tx + b) : 0.f;
             if (i0 + 16 * warp < I) {
+                float* row0 = C + (int64_t)(i0 + 8 * ty) * c_si + (int64_t)(j0 + 4 * tx) * c_sj;
+                if (accumulate) {   // all loads first: between stores the compiler must assume aliasing and would serialise them
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (i0 + 8 * ty + a < I && j0 + 4 * tx + b < J) acc[a][b] += __ldcg(row0 + (int64_t)a * c_si + b * c_sj);
+                }
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
-                    const int i = i0 + 8 * ty + a;
-                    float* row = C + (int64_t)i * c_si + (int64_t)(j0 + 4 * tx) * c_sj;
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        if (i < I && j0 + 4 * tx + b < J) {
+                        if (i0 + 8 * ty + a < I && j0 + 4 * tx + b < J) {
                             float v = acc[a][b];
-                            if (accumulate) v += __ldcg(row + b * c_sj);
                             if (bias) v += bj[b];
-                            __stcg(row + b * c_sj, g_act(act, slope, v));
+                            __stcg(row0 + (int64_t)a * c_si + b * c_sj, g_act(act, slope, v));
                         }
                     }
                 }
@@ -258,7 +270,7 @@ __device__ __noinline__ void g_thinj_fwd(const GLayer& l, const float* __restric
                     acc[2] = fmaf(x, w.z, acc[2]); acc[3] = fmaf(x, w.w, acc[3]);
                 };
                 if (vec) {
-#pragma unroll 4
+#pragma unroll 8
                     for (int k = 0; k < kn; k += 4) {
                         const float4 x4 = __ldcg(reinterpret_cast<const float4*>(xr + k));
                         mac(k, x4.x); mac(k + 1, x4.y); mac(k + 2, x4.z); mac(k + 3, x4.w);
@@ -451,7 +463,7 @@ __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars&
     const float neg_step = (float)(-(ls.lr / bc1));
     const float bc2s = (float)sqrt(bc2);
     {
-        constexpr int UN = 4;   // parameters in flight per thread (5 loads each)
+        constexpr int UN = 8;   // parameters in flight per thread (5 loads each)
         for (int p0 = threadIdx.x; p0 < n.P; p0 += UN * kGThreads) {
             float g[UN], m[UN], v[UN], th[UN], tt[UN];
 #pragma unroll
