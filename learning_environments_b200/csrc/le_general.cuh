@@ -55,6 +55,10 @@ __device__ __forceinline__ void cp_async4_zfill(uint32_t saddr, const void* gptr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(gptr), "r"(valid ? 4 : 0) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+
 __device__ __forceinline__ float g_act(int act, float slope, float z) {
     if (act == 1) return tanh_one(z);
     if (act == 2) return fmaxf(z, slope * z);
@@ -99,23 +103,30 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
         const float* b = B + (int64_t)(l0 + lb) * b_sl + (int64_t)(j0 + jb) * b_sj;
         const uint32_t sa = sm_u32 + 4u * (uint32_t)(buf * TK * LDA + sA0);
         const uint32_t sb = sm_u32 + 4u * (uint32_t)(2 * TK * LDA + buf * TK * LDB + sB0);
+        if (i0 + TM <= I && j0 + TN <= J && l0 + TK <= L) {   // interior chunk: no bounds tests, pointer increments only
 #pragma unroll
-        for (int q = 0; q < NA; ++q) {
-            const bool ok = i0 + ia + q * dia < I && l0 + la + q * dla < L;
-            cp_async4_zfill(sa + 4u * (uint32_t)(q * sdA), ok ? a + q * gdA : A, ok);
-        }
+            for (int q = 0; q < NA; ++q) { cp_async4(sa + 4u * (uint32_t)(q * sdA), a); a += gdA; }
 #pragma unroll
-        for (int q = 0; q < NB; ++q) {
-            const bool ok = j0 + jb + q * djb < J && l0 + lb + q * dlb < L;
-            cp_async4_zfill(sb + 4u * (uint32_t)(q * sdB), ok ? b + q * gdB : B, ok);
+            for (int q = 0; q < NB; ++q) { cp_async4(sb + 4u * (uint32_t)(q * sdB), b); b += gdB; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NA; ++q) {
+                const bool ok = i0 + ia + q * dia < I && l0 + la + q * dla < L;
+                cp_async4_zfill(sa + 4u * (uint32_t)(q * sdA), ok ? a + q * gdA : A, ok);
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const bool ok = j0 + jb + q * djb < J && l0 + lb + q * dlb < L;
+                cp_async4_zfill(sb + 4u * (uint32_t)(q * sdB), ok ? b + q * gdB : B, ok);
+            }
         }
         cp_async_commit();
     };
-    float acc[8][4];
+    float2 acc[8][2];   // packed fp32x2 accumulators: (a, 2c) and (a, 2c+1) share one FFMA2
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int c = 0; c < 2; ++c) acc[a][c] = make_float2(0.f, 0.f);
     issue(0, 0, 0, 0);
     cp_async_wait<0>();
     __syncthreads();
@@ -141,11 +152,12 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
                     na1 = *reinterpret_cast<const float4*>(as + (l + 1) * LDA + 4);
                     nb4 = *reinterpret_cast<const float4*>(bs + (l + 1) * LDB);
                 }
-                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float2 bv[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
 #pragma unroll
                 for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                    for (int c = 0; c < 2; ++c) acc[a][c] = __ffma2_rn(make_float2(av[a], av[a]), bv[c], acc[a][c]);
                 a0 = na0; a1 = na1; b4 = nb4;
             }
         }
@@ -160,14 +172,17 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
                     for (int a = 0; a < 8; ++a)
 #pragma unroll
                         for (int b = 0; b < 4; ++b)
-                            if (i0 + 8 * ty + a < I && j0 + 4 * tx + b < J) acc[a][b] += __ldcg(row0 + (int64_t)a * c_si + b * c_sj);
+                            if (i0 + 8 * ty + a < I && j0 + 4 * tx + b < J) {
+                                const float old = __ldcg(row0 + (int64_t)a * c_si + b * c_sj);
+                                if (b & 1) acc[a][b >> 1].y += old; else acc[a][b >> 1].x += old;
+                            }
                 }
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         if (i0 + 8 * ty + a < I && j0 + 4 * tx + b < J) {
-                            float v = acc[a][b];
+                            float v = (b & 1) ? acc[a][b >> 1].y : acc[a][b >> 1].x;
                             if (bias) v += bj[b];
                             __stcg(row0 + (int64_t)a * c_si + b * c_sj, g_act(act, slope, v));
                         }
@@ -177,7 +192,7 @@ __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                for (int c = 0; c < 2; ++c) acc[a][c] = make_float2(0.f, 0.f);
         }
         it = nit; jt = njt; lc = nlc;
         cp_async_wait<0>();
