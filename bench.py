@@ -37,7 +37,8 @@ WORKLOADS = {
     "sweep_h1024": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=64, train_episodes=2, env_hidden=1024, grad_evals=128),
     # DuelingDDQN inner loops (general CTA-per-lane kernel): CartPole yaml section, Acrobot section of default_config_acrobot.yaml
     "cartpole_se_dueling": dict(cfg="cartpole_syn_env", kind="se", agent="duelingddqn", members_per_gpu=296, train_episodes=3),
-    "acrobot_se_dueling": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=148, train_episodes=2, init_episodes=1),
+    # 197 members x 3 lanes = 591 lanes = two full waves of the 296 resident CTAs
+    "acrobot_se_dueling": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=197, train_episodes=2, init_episodes=1),
 }
 
 
