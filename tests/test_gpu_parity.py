@@ -344,3 +344,64 @@ def test_general_kernel_edge_cases_vs_oracle(ops):
         same = res["train_steps"] == oracle["train_steps"]
         assert same.mean() >= 0.66, (over, res["train_steps"], oracle["train_steps"])
         assert np.array_equal(res["timed_out"], oracle["timed_out"]), over
+
+
+# ---- BASELINE-size runs: properties that do not need the (slow) CPU restatement ---------------------------------------
+def _full_size_run(ops, cfg, theta, keys, env_index=None, n_env=1):
+    bufs = _run_fused(ops, cfg, theta, keys, None, n_env=n_env, env_index=env_index)
+    res = bufs.results()
+    return res, bufs.rewards.cpu().numpy(), bufs.q_final.cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["cartpole_se", "cartpole_se_dueling"])
+def test_full_size_population_is_deterministic_and_independent_of_scheduling(ops, tag):
+    """bench.py's lane count (one full residency wave + a ragged second one) at the yaml batch size.  (1) the same launch
+    twice is bit-identical; (2) a lane's result does not depend on which slot runs it, how many lanes share the GPU or
+    the order of the lane queue (run a permuted subset alone); (3) every lane made progress and the bookkeeping is
+    consistent (learn_iters = steps after the init episodes, episode lengths sum to train_steps)."""
+    g = load_golden("trajectory_%s.npz" % tag)
+    cfg = cfg_from_bytes(g["cfg"])
+    dueling = tag.endswith("dueling")
+    cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = (2, 3, 1) if dueling else (6, 10, 1)
+    n_env = 8
+    n = 148 * 2 + 37 if dueling else 148 * 8 * 2 + 101
+    rng = np.random.RandomState(5)
+    thetas = (g["env_theta"][None] + rng.standard_normal((n_env, g["env_theta"].size)).astype(np.float32) * 0.02).astype(np.float32)
+    keys = [philox.lane_key(31, 2, i, i % 3, 0) for i in range(n)]
+    env_index = (np.arange(n) % n_env).astype(np.int32)
+    r1, rew1, q1 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
+    r2, rew2, q2 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
+    for f in ("n_episodes", "train_steps", "learn_iters", "test_steps", "score"):
+        assert np.array_equal(r1[f], r2[f]), f
+    assert np.array_equal(rew1, rew2) and np.array_equal(q1, q2)
+    sub = rng.permutation(n)[:53]
+    r3, rew3, q3 = _full_size_run(ops, cfg, thetas, [keys[i] for i in sub], env_index[sub], n_env)
+    for f in ("n_episodes", "train_steps", "learn_iters", "test_steps", "score"):
+        assert np.array_equal(r3[f], r1[f][sub]), f
+    assert np.array_equal(rew3, rew1[sub]) and np.array_equal(q3, q1[sub])
+    assert (r1["n_episodes"] >= 1).all() and (r1["train_steps"] >= r1["n_episodes"]).all()
+    lengths = _run_fused(ops, cfg, thetas, [keys[i] for i in sub], None, n_env=n_env, env_index=env_index[sub]).lengths.cpu().numpy()
+    assert np.array_equal(lengths.sum(1), r3["train_steps"])
+    first = lengths[:, 0]
+    assert np.array_equal(r3["learn_iters"], r3["train_steps"] - first)         # init_episodes = 1: every later step learns
+    assert np.isfinite(q1).all() and np.isfinite(r1["score"]).all()
+
+
+def test_full_size_mirrored_lanes_with_zero_noise_agree(ops):
+    """NES mirrored sampling at sigma = 0: theta+eps and theta-eps are the same environment, so lanes that share a
+    lane key must return the same score through different env slots (encode -> perturb -> evaluate round trip)."""
+    g = load_golden("trajectory_cartpole_se.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 4, 5, 1
+    pop = 64
+    theta = torch.from_numpy(g["env_theta"]).cuda()
+    thetas = ops.nes_perturb(theta, pop, 0, pop, 77, 3, 0.0).reshape(pop, 3, -1)          # rows (theta, +eps, -eps), sigma = 0
+    assert torch.equal(thetas[:, 0], thetas[:, 1]) and torch.equal(thetas[:, 0], thetas[:, 2])
+    keys = [philox.lane_key(77, 3, m, 0, 0) for m in range(pop) for _ in range(3)]
+    env_index = np.arange(pop * 3, dtype=np.int32)
+    bufs = ops.InnerLoopBuffers(cfg, pop * 3, pop * 3, "cuda")
+    ops.inner_loop_run(bufs, cfg, thetas.reshape(pop * 3, -1).contiguous(), dev(env_index), ops.keys_tensor(keys, "cuda"))
+    torch.cuda.synchronize()
+    sc = bufs.results()["score"].reshape(pop, 3)
+    assert np.array_equal(sc[:, 0], sc[:, 1]) and np.array_equal(sc[:, 0], sc[:, 2])
+    assert len(np.unique(sc[:, 0])) > 4           # different members (keys) do differ
