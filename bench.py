@@ -39,6 +39,9 @@ WORKLOADS = {
     "cartpole_se_dueling": dict(cfg="cartpole_syn_env", kind="se", agent="duelingddqn", members_per_gpu=296, train_episodes=3),
     # 197 members x 3 lanes = 591 lanes = two full waves of the 296 resident CTAs
     "acrobot_se_dueling": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=197, train_episodes=2, init_episodes=1),
+    # BASELINE config 4 (vary_hp evaluation): 4096 DDQN agents per GPU with per-lane lr / batch_size / hidden_size / hidden_layer
+    # on ONE fixed CartPole SE, init_episodes=10, plateau early-out; train_episodes bounded (the evaluator's cap is 1000)
+    "vary_hp": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=4096, train_episodes=30),
 }
 
 
@@ -204,6 +207,119 @@ def workload_config(name, cfg, members_per_gpu, plan):
     return c
 
 
+def run_vary_hp_workload(args):
+    """--workload vary_hp: BASELINE config 4.  One step = every agent of this rank trained on the SE (virtual-env plateau rule)
+    and tested on the real env: one launch of the register kernel (hidden_layer <= 1, hidden_size <= 128) and one of the
+    general kernel (the rest), per-lane le_lane_cfg."""
+    import torch
+    import torch.distributed as dist
+    from learning_environments_b200 import default_configs, ops, vary_hp
+    from learning_environments_b200.rng import lane_keys
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    w = WORKLOADS["vary_hp"]
+    d = default_configs.get(w["cfg"])
+    n = args.members_per_gpu or w["members_per_gpu"]
+    over = dict(vary_hp.OVERRIDES, train_episodes=w["train_episodes"])
+    cfgs = vary_hp.sample_agent_cfgs(d, n, np.random.RandomState(1000 + rank), over, True, None)
+    theta_host = synthetic_theta(cfgs[0])
+    theta_dev = torch.from_numpy(theta_host).to(dev).reshape(1, -1)
+    groups = []
+    for resident in (True, False):
+        idx = np.array([i for i, c in enumerate(cfgs) if c.q_is_register_resident() == resident], int)
+        if len(idx):
+            sub = [cfgs[i] for i in idx]
+            cfg0 = vary_hp._max_cfg(sub)
+            groups.append(dict(idx=idx, sub=sub, cfg0=cfg0, bufs=ops.InnerLoopBuffers(cfg0, len(idx), 1, dev, n_cfg=len(idx))))
+    total = args.warmup + args.steps
+    keys = [torch.from_numpy(lane_keys(4321, g, rank * n + np.arange(n), np.zeros(n, int), np.zeros(n, int)).view(np.int32).copy()).to(dev)
+            for g in range(total)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ffma_peak = ops.bench_ffma()
+
+    def step(g):
+        for gr in groups:
+            ops.inner_loop_run(gr["bufs"], gr["sub"], theta_dev, None, keys[g][torch.from_numpy(gr["idx"]).to(dev)].contiguous(), cfg0=gr["cfg0"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for g in range(args.warmup):
+        step(g)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_ms, steps_done, flop = 0.0, 0, 0.0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(args.warmup + k)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms += e0.elapsed_time(e1)
+        for gr in groups:
+            res = gr["bufs"].results()
+            steps_done += int(res["train_steps"].sum())
+            for c, st, li in zip(gr["sub"], res["train_steps"], res["learn_iters"]):
+                a, b = f_parts(c)
+                flop += float(st) * a + float(li) * b
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms, float(steps_done), flop], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, steps_all, flop_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        steps_all, flop_all = float(steps_done), flop
+    # end to end through the public API: sampling, H2D of theta / keys / per-lane cfgs, both launches, D2H of the results
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for k in range(args.steps):
+        _, st, _, _ = vary_hp.evaluate_agents(d, theta_host.reshape(1, -1), n, seed=1000 + rank, overrides=over, device=dev)
+        e2e_steps += sum(st[0])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, float(e2e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        a, b = te.clone(), te.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_steps = float(a[0]), float(b[1])
+    if rank == 0:
+        achieved = flop_all / world / (dev_ms * 1e-3) / 1e12
+        n_gen = sum(len(g["idx"]) for g in groups if not g["cfg0"].q_is_register_resident())
+        line = {
+            "metric": "se_env_steps_per_s", "value": steps_all / (dev_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "vary_hp: %d DDQN_vary agents per GPU on one CartPole SE (lr, batch_size in [66,597], hidden_size in "
+                                   "[19,171], hidden_layer in {1,2} per lane), init_episodes=10, <=%d train episodes, plateau early-out, "
+                                   "final test() of 10 real-env episodes" % (n, w["train_episodes"]),
+                       "agents_per_gpu": n, "general_kernel_lanes": n_gen, "l2": "256 MiB buffer written between timed steps (L2 flush)"},
+            "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s",
+                    "h2d_bytes_per_step": int(theta_host.nbytes + n * 8 + n * 200), "d2h_bytes_per_step": int(n * (40 + 10 * 8))},
+            "gpu_launches": (1 + len(groups)) * args.steps, "clocks": clocks,
+            "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / ffma_peak if ffma_peak else None, "traffic": None,
+                         "peak_source": "le_bench_ffma microbenchmark in this run"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,6 +334,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "vary_hp":
+        return run_vary_hp_workload(args)
 
     import torch
     import torch.distributed as dist
