@@ -471,7 +471,7 @@ __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars&
         const int xs = i > 0 ? S : SDs;
         g_layer_bwd(l, w.theta, w.grad, X, xs, w.actA, w.dact, S, B, i > 0 ? w.dact + n.feat[i - 1].y_off : nullptr, S, false, n.slope, sm);
     }
-    // Adam + Polyak (same operation order as LaneCore::adam_one)
+    // Adam + Polyak (same operation order as LaneCore::adam_polyak)
     ls.b1pow *= ls.beta1;
     ls.b2pow *= ls.beta2d;
     const double bc1 = 1.0 - ls.b1pow, bc2 = 1.0 - ls.b2pow;
