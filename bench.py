@@ -30,7 +30,7 @@ import numpy as np  # noqa: E402
 # workload name -> (default_configs name, env kind, members per GPU, bounded train_episodes)
 WORKLOADS = {
     "cartpole_se": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=10),
-    "acrobot_se": dict(cfg="acrobot_syn_env", kind="se", members_per_gpu=592, train_episodes=3, init_episodes=1),
+    "acrobot_se": dict(cfg="acrobot_syn_env", kind="se", members_per_gpu=1184, train_episodes=3, init_episodes=1),
     "cartpole_rn": dict(cfg="cartpole_reward_env", kind="rn", members_per_gpu=1184, train_episodes=40),
     # BASELINE config 5 (scaling sweep): SE hidden width 1024, 257 lanes per member (theta + 128 x (+eps, -eps) evaluations);
     # 64 members per GPU = population 512 x 256 envs on 8 GPUs

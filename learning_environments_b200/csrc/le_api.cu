@@ -260,9 +260,9 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
     } else {
         int per_sm = ops->inner_max_ctas_per_sm();
         if (per_sm < 1) per_sm = 1;
-        const int want = (n_lanes + kWarpsPerCta - 1) / kWarpsPerCta;
+        const int want = (n_lanes + ops->inner_warps - 1) / ops->inner_warps;
         pl->grid = want < sms * per_sm ? want : sms * per_sm;
-        pl->slots = pl->grid * kWarpsPerCta;
+        pl->slots = pl->grid * ops->inner_warps;
         pl->ring_stride_f = (int64_t)pl->ring_cap * ops->ring_row_floats();
     }
     const int64_t pv4 = c->env_kind == LE_ENV_SE ? ops->se_pack_vec4(c->env_hidden) : (c->env_kind == LE_ENV_RN ? ops->rn_pack_vec4(c->env_hidden) : 1);

@@ -496,8 +496,10 @@ __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars&
                     vv = vv + (ls.w2 * g[u]) * g[u];
                     __stcg(w.m + p, mm);
                     __stcg(w.v + p, vv);
-                    const float denom = __fdiv_rn(__fsqrt_rn(vv), bc2s) + ls.eps;
-                    const float pn = th[u] + __fdiv_rn(neg_step * mm, denom);
+                    bool exact = true;
+                    float up = adam_update_core(mm, vv, neg_step, bc2s, ls.eps, &exact);
+                    if (!exact) up = __fdiv_rn(neg_step * mm, __fdiv_rn(__fsqrt_rn(vv), bc2s) + ls.eps);
+                    const float pn = th[u] + up;
                     __stcg(w.theta + p, pn);
                     __stcg(w.thetaT + p, ls.tau * pn + ls.one_minus_tau * tt[u]);
                 }

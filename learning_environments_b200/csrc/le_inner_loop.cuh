@@ -28,6 +28,12 @@ struct RunParams {
 #define LE_WARPS_PER_CTA 4
 #endif
 constexpr int kWarpsPerCta = LE_WARPS_PER_CTA;
+// Fused kernel: U <= 2 -> 2 CTAs x 4 warps per SM (<= 255 registers each); U = 4 needs all 255 registers per thread, so ONE
+// CTA of 8 warps fills the register file (8 x 32 x 255) and still gives every scheduler two warps to alternate between.
+#ifndef LE_WARPS_U4
+#define LE_WARPS_U4 8
+#endif
+template <int U> constexpr int inner_warps() { return U <= 2 ? kWarpsPerCta : LE_WARPS_U4; }
 
 
 // Per-warp shared memory: [stage rows | test-phase weight image (aliased)] [Adam m, v] [lane configuration] [reduction]
@@ -364,11 +370,11 @@ struct FusedLane {
 #define LE_MIN_CTAS_U2 2
 #endif
 template <int SD, int AD, int U, int ACT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (U <= 2 ? LE_MIN_CTAS_U2 : 1)) inner_loop_kernel(const RunParams P) {
+__global__ void __launch_bounds__(inner_warps<U>() * 32, (U <= 2 ? LE_MIN_CTAS_U2 : 1)) inner_loop_kernel(const RunParams P) {
     using SW = SmemWarp<SD, AD, U>;
     extern __shared__ __align__(16) float smem_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kWarpsPerCta + warp;
+    const int slot = blockIdx.x * inner_warps<U>() + warp;
     float* smem = smem_dyn + warp * SW::FLOATS;
     for (;;) {
         int lane_id = 0;

@@ -8,6 +8,7 @@ namespace le {
 
 struct InstanceOps {
     int sd, ad, units, act;  // act: QACT_TANH / QACT_LEAKY
+    int inner_warps;         // warps (= lane slots) per CTA of the fused kernel
     // fused persistent kernel
     int (*inner_max_ctas_per_sm)();
     cudaError_t (*launch_inner)(const RunParams& P, int grid, cudaStream_t st);
@@ -156,17 +157,20 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
 // ------------------------------------------------------------------------------------------------------
 template <int SD, int AD, int U, int ACT>
 struct InstanceImpl {
-    static constexpr size_t kSmemBytes = (size_t)kWarpsPerCta * SmemWarp<SD, AD, U>::FLOATS * sizeof(float);
+    static constexpr size_t kSmemBytes = (size_t)kWarpsPerCta * SmemWarp<SD, AD, U>::FLOATS * sizeof(float);          // unit kernels
+    static constexpr int kInnerWarps = inner_warps<U>();
+    static constexpr size_t kInnerSmemBytes = (size_t)kInnerWarps * SmemWarp<SD, AD, U>::FLOATS * sizeof(float);      // fused kernel
+    static_assert(kInnerSmemBytes <= 227 * 1024, "per-CTA shared memory of the fused kernel exceeds 227 KB");
     static int inner_max_ctas_per_sm() {
         int nb = 0;
-        cudaFuncSetAttribute(inner_loop_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, inner_loop_kernel<SD, AD, U, ACT>, kWarpsPerCta * 32, kSmemBytes);
+        cudaFuncSetAttribute(inner_loop_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInnerSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, inner_loop_kernel<SD, AD, U, ACT>, kInnerWarps * 32, kInnerSmemBytes);
         return nb;
     }
     static cudaError_t launch_inner(const RunParams& P, int grid, cudaStream_t st) {
-        cudaError_t e = cudaFuncSetAttribute(inner_loop_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(inner_loop_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInnerSmemBytes);
         if (e != cudaSuccess) return e;
-        inner_loop_kernel<SD, AD, U, ACT><<<grid, kWarpsPerCta * 32, kSmemBytes, st>>>(P);
+        inner_loop_kernel<SD, AD, U, ACT><<<grid, kInnerWarps * 32, kInnerSmemBytes, st>>>(P);
         return cudaGetLastError();
     }
     static int64_t ring_row_floats() { return RowLayout<SD>::ROWF; }
@@ -215,7 +219,7 @@ struct InstanceImpl {
         return cudaGetLastError();
     }
     static const InstanceOps* ops() {
-        static const InstanceOps o = {SD, AD, U, ACT, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
+        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
                                       rn_pack_vec4, launch_pack_se, launch_pack_rn, launch_se_forward, launch_rn_reward,
                                       launch_qnet_forward, launch_td_update};
         return &o;
