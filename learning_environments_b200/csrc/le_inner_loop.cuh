@@ -47,7 +47,7 @@ struct SmemWarp {
     static constexpr int BUF_F = STAGE_F > QW_F ? STAGE_F : QW_F;
     static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
     static constexpr int CFG_F = (sizeof(le_lane_cfg) + 15) / 16 * 4;
-    static constexpr int RED_F = 2 * (U <= 2 ? 8 : 4) * (1 + AD) * 32 * 2;  // LaneCore::RED_F: two cross-lane reduction buffers
+    static constexpr int RED_F = 2 * (U <= 2 ? LE_R_U2 : 4) * (1 + AD) * 32 * 2;  // LaneCore::RED_F: two cross-lane reduction buffers
     static constexpr int FLOATS = BUF_F + MV_F + CFG_F + RED_F;
     static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F, OFF_RED = BUF_F + MV_F + CFG_F;
 };
