@@ -57,16 +57,12 @@ class LaneLayout(object):
         if grad_eval_type not in ("mean", "minmax"):
             raise NotImplementedError("Unknown parameter for grad_eval_type: " + str(grad_eval_type))
         red = np.mean if grad_eval_type == "mean" else np.min
-        sc = out["score"]
-        orig = np.zeros(self.n_members)
-        add = np.zeros(self.n_members)
-        sub = np.zeros(self.n_members)
-        for m in range(self.n_members):
-            sel = self.lane_member == self.member_lo + m
-            orig[m] = sc[sel & (self.lane_variant == 0)][0]
-            add[m] = red(sc[sel & (self.lane_variant == 1)])
-            if self.mirrored:
-                sub[m] = red(sc[sel & (self.lane_variant == 2)])
+        # lanes are member-major: [theta | +eps x num_grad_evals | -eps x num_grad_evals] per member
+        E = self.num_grad_evals
+        sc = np.asarray(out["score"], np.float64).reshape(self.n_members, self.lanes_per_member)
+        orig = sc[:, 0].copy()
+        add = red(sc[:, 1:1 + E], axis=1)
+        sub = red(sc[:, 1 + E:1 + 2 * E], axis=1) if self.mirrored else np.zeros(self.n_members)
         return orig, add, sub
 
 
