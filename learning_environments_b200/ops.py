@@ -176,7 +176,9 @@ def inner_loop_run(bufs, cfgs, env_theta, env_index, keys, q_init=None, trace_la
     n_cfg = len(cfgs)
     assert n_cfg in (1, bufs.n_lanes) and bufs.cfg_dev.shape[0] == n_cfg
     raw = b"".join(bytes(c) for c in cfgs)
-    bufs.cfg_dev.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8).reshape(n_cfg, -1), non_blocking=False)
+    if getattr(bufs, "_cfg_raw", None) != raw:      # lane configurations rarely change between generations: upload once
+        bufs.cfg_dev.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8).reshape(n_cfg, -1), non_blocking=False)
+        bufs._cfg_raw = raw
     keys = _dev(keys, _I32)
     assert keys.numel() == 2 * bufs.n_lanes
     tr = None
