@@ -120,6 +120,8 @@ def gen_td_update(yaml_name, tag, seed, steps=5, agent=None, **overrides):
     import torch
     mods = rh.import_reference()
     cfg, agent_name = small_config(yaml_name, agent, **overrides)
+    if env_overrides:
+        cfg["envs"][cfg["env_name"]].update(env_overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     real_env = fac.generate_real_env()
@@ -189,11 +191,13 @@ def gen_real_env(seed):
         np.savez(os.path.join(GOLDEN, "real_env_%s.npz" % tag), n_episodes=len(eps), **flat)
 
 
-def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, use_test_env=True, agent=None):
+def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, use_test_env=True, agent=None, env_overrides=None):
     """Full BaseAgent.train(+test) of the reference under RNG injection; per-step trace of the first steps."""
     import torch
     mods = rh.import_reference()
     cfg, agent_name = small_config(yaml_name, agent, **overrides)
+    if env_overrides:
+        cfg["envs"][cfg["env_name"]].update(env_overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     real_env = fac.generate_real_env()
@@ -361,6 +365,30 @@ def main():
                                                                trace_cap=300)),
         ("trajectory_acrobot_real", lambda: gen_trajectory(AC, "acrobot_real", 19, (0x67, 0x68), "real",
                                                            dict(train_episodes=2, test_episodes=1, init_episodes=1), trace_cap=700)),
+        # general-kernel lanes end to end: Acrobot yaml DuelingDDQN (2 x 128 relu, feature_dim 128), 2-hidden-layer DDQN
+        ("trajectory_acrobot_se_dueling", lambda: gen_trajectory("default_config_acrobot.yaml", "acrobot_se_dueling", 22, (0x71, 0x72), "se",
+                                                                 dict(train_episodes=2, test_episodes=1, init_episodes=1), trace_cap=500,
+                                                                 agent="DuelingDDQN")),
+        ("trajectory_cartpole_se_ddqn_l2", lambda: gen_trajectory(CP, "cartpole_se_ddqn_l2", 23, (0x73, 0x74), "se",
+                                                                  dict(train_episodes=3, test_episodes=2, init_episodes=1, hidden_layer=2,
+                                                                       hidden_size=150), trace_cap=300)),
+        # hidden_layer = 0 builds the same net as 1 (models/model_utils.py:34); reward types 1 / 5 / 6 through the whole loop;
+        # the real-env early-out rule (agents/base_agent.py:49-62) firing
+        ("trajectory_cartpole_se_h0", lambda: gen_trajectory(CP, "cartpole_se_h0", 24, (0x75, 0x76), "se",
+                                                             dict(train_episodes=3, test_episodes=2, init_episodes=1, hidden_layer=0),
+                                                             trace_cap=300)),
+        ("trajectory_cartpole_rn_t1", lambda: gen_trajectory(RN, "cartpole_rn_t1", 25, (0x77, 0x78), "rn",
+                                                             dict(train_episodes=8, test_episodes=1, init_episodes=2), trace_cap=200,
+                                                             env_overrides=dict(reward_env_type=1))),
+        ("trajectory_cartpole_rn_t5", lambda: gen_trajectory(RN, "cartpole_rn_t5", 26, (0x79, 0x7A), "rn",
+                                                             dict(train_episodes=8, test_episodes=1, init_episodes=2), trace_cap=200,
+                                                             env_overrides=dict(reward_env_type=5))),
+        ("trajectory_cartpole_rn_t6", lambda: gen_trajectory(RN, "cartpole_rn_t6", 27, (0x7B, 0x7C), "rn",
+                                                             dict(train_episodes=8, test_episodes=1, init_episodes=2), trace_cap=200,
+                                                             env_overrides=dict(reward_env_type=6))),
+        ("trajectory_cartpole_real_solved", lambda: gen_trajectory(CP, "cartpole_real_solved", 28, (0x7D, 0x7E), "real",
+                                                                   dict(train_episodes=12, test_episodes=2, init_episodes=1, early_out_num=2),
+                                                                   trace_cap=300, env_overrides=dict(solved_reward=9.9))),
         ("nes_cartpole", lambda: gen_nes(21)),
     ]
     want = sys.argv[1:]

@@ -141,7 +141,8 @@ def _run_fused(ops, cfg, env_theta, keys, q_init, trace_cap=0, n_env=1, env_inde
 
 
 @pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling", "cartpole_se_k2",
-                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real"])
+                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real", "acrobot_se_dueling", "cartpole_se_ddqn_l2",
+                                 "cartpole_se_h0", "cartpole_rn_t1", "cartpole_rn_t5", "cartpole_rn_t6", "cartpole_real_solved"])
 def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
     """The fused persistent kernel, one lane, against the reference's own BaseAgent.train trace."""
     g = load_golden("trajectory_%s.npz" % tag)
