@@ -53,10 +53,12 @@ def small_config(name, agent_name=None, **agent_overrides):
 
 
 # ------------------------------------------------------------------------------------------------------
-def gen_se_step(yaml_name, tag, seed):
+def gen_se_step(yaml_name, tag, seed, env_overrides=None):
     import torch
     mods = rh.import_reference()
     cfg = rh.load_reference_yaml(yaml_name)
+    if env_overrides:
+        cfg["envs"][cfg["env_name"]].update(env_overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     venv = fac.generate_virtual_env()
@@ -332,6 +334,11 @@ def main():
     jobs = [
         ("se_step_cartpole", lambda: gen_se_step(CP, "cartpole", 1)),
         ("se_step_acrobot", lambda: gen_se_step(AC, "acrobot", 2)),
+        # the other activation functions of models/model_utils.py:9-19 and other hidden widths for the SE
+        ("se_step_cartpole_tanh", lambda: gen_se_step(CP, "cartpole_tanh", 31, dict(activation_fn="tanh", hidden_size=96))),
+        ("se_step_cartpole_relu", lambda: gen_se_step(CP, "cartpole_relu", 32, dict(activation_fn="relu", hidden_size=32))),
+        ("se_step_acrobot_identity", lambda: gen_se_step(AC, "acrobot_identity", 33, dict(activation_fn="identity", hidden_size=40))),
+        ("se_step_acrobot_leaky", lambda: gen_se_step(AC, "acrobot_leaky", 34, dict(activation_fn="leakyrelu", hidden_size=300))),
         ("rn_reward_cartpole", lambda: gen_rn_reward(3)),
         ("td_update_cartpole", lambda: gen_td_update(CP, "cartpole", 4)),
         ("td_update_acrobot", lambda: gen_td_update(AC, "acrobot", 5)),

@@ -29,7 +29,7 @@ def dev(a, dtype=None):
     return t.cuda()
 
 
-@pytest.mark.parametrize("tag", ["cartpole", "acrobot"])
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_tanh", "cartpole_relu", "acrobot_identity", "acrobot_leaky"])
 def test_se_forward_vs_reference_golden(ops, tag):
     g = load_golden("se_step_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])

@@ -10,7 +10,7 @@ from tests.helpers import assert_params_close, cfg_from_bytes, load_golden, rel_
 RTOL = 1e-5
 
 
-@pytest.mark.parametrize("tag", ["cartpole", "acrobot"])
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_tanh", "cartpole_relu", "acrobot_identity", "acrobot_leaky"])
 def test_se_step(tag):
     g = load_golden("se_step_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
