@@ -22,10 +22,10 @@ import torch.nn as nn
 
 from . import config as le_config
 from . import ops
-from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, Q_DQN, Q_DUELING, REAL_ENV_IDS, LaneCfg
+from ._abi import ACT_IDS, ENV_REAL, Q_DQN, Q_DUELING, REAL_ENV_IDS, LaneCfg
 from .envs import EnvFactory, EnvWrapper, _cuda_device, build_nn_from_config
 from .rng import lane_keys
-from .utils import ReplayBuffer, to_one_hot_encoding
+from .utils import ReplayBuffer
 
 #: training env steps per second assumed when a wall-clock `time_remaining` is mapped onto the deterministic
 #: step budget of the kernel (the reference's time budget is wall-clock on one CPU core: ~800 steps/s).

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._abi import ENV_REAL, LaneCfg
+from ._abi import LaneCfg
 from .rng import lane_keys
 
 

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import ops
 from ._abi import ACT_IDS, ENV_REAL, ENV_RN, ENV_SE, REAL_ENV_IDS
-from .config import ENV_DIMS, env_kwargs
+from .config import ENV_DIMS
 from .utils import from_one_hot_encoding, to_one_hot_encoding
 
 

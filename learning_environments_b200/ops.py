@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import ENV_REAL, ENV_RN, ENV_SE, LaneCfg, LaneOut, Trace, check
+from ._abi import LaneCfg, LaneOut, Trace, check
 
 _F32, _I32, _F64 = torch.float32, torch.int32, torch.float64
 

@@ -15,7 +15,7 @@ import torch
 
 from . import config as le_config
 from . import ops
-from ._abi import ENV_REAL, ENV_SE, LaneCfg
+from ._abi import ENV_REAL, ENV_SE
 from .agents import vary_hyperparameters
 from .rng import lane_keys
 
