@@ -288,3 +288,30 @@ def test_run_vary_hp_all_models_in_one_launch(le, tmp_path):
     d0 = torch.load(f0, weights_only=False)
     assert len(d0["reward_list"]) == 4 and list(d0["env_reward_overview"].index) == ["CartPole-v0_0", "CartPole-v0_1"]
     assert all(1 <= e[0] <= 4 for e in d0["episode_length_needed"])
+
+
+def test_integration_md_ctypes_stub_runs_as_written(le):
+    """The reference-side binding shown in INTEGRATION.md (section 2) is executed verbatim: host buffers in, scores out."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(.*?)```", text, re.S).group(1)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)                      # the stub loads the library by its repo-relative path
+    try:
+        exec(compile(code, "INTEGRATION.md", "exec"), ns)
+        cfg = _small(le)
+        lane = le["agents"].le_config.lane_cfg(cfg, "ddqn", 0)
+        stub_cfg = ns["LaneCfg"].from_buffer_copy(bytes(lane))
+        assert ns["lib"].le_sizeof_lane_cfg() == len(bytes(lane))
+        torch.manual_seed(2)
+        theta = le["envs"].EnvFactory(cfg).generate_virtual_env().env.theta().numpy()[None].copy()
+        keys = np.array([[5, 6], [7, 8], [9, 10]], np.uint32)
+        scores, rewards, lengths = ns["calc_scores"](stub_cfg, theta, np.zeros(3, np.int32), keys)
+    finally:
+        os.chdir(cwd)
+    for i in range(3):
+        want = c_oracle.run_lane(lane, theta[0], (int(keys[i, 0]), int(keys[i, 1])))
+        assert lengths[i, 0] == want["lengths"][0]                     # pre-learning episode: exact
+    assert np.isfinite(scores).all() and (lengths[:, 0] > 0).all()
