@@ -80,7 +80,7 @@ typedef struct le_lane_cfg {
     int32_t env_act;        /* LE_ACT_* of the SE / RN nets                                            */
     float env_slope[3];     /* leaky/prelu slope per net (state,reward,done) or [0] for the RN         */
     int32_t rn_type;        /* reward_env_type 0,1,2,5,6 (envs/reward_env.py:84-110)                   */
-    int32_t q_hidden;       /* Critic_DQN hidden width (hidden_layer <= 1)                             */
+    int32_t q_hidden;       /* hidden width of the Q-net / dueling feature stream (see q_layers)       */
     int32_t q_act;          /* LE_ACT_TANH | RELU | LEAKYRELU                                          */
     int32_t batch_size;     /* agents/DDQN.py:24                                                       */
     int32_t rb_size;        /* replay ring capacity (utils.py:10)                                      */
@@ -103,7 +103,7 @@ typedef struct le_lane_cfg {
 typedef struct le_lane_out {
     int32_t n_episodes;     /* len(reward_list) before timeout padding                                 */
     int32_t timed_out;      /* step_budget hit (time_is_up analog, agents/base_agent.py:30-47)         */
-    int64_t train_steps;    /* env steps taken in training                                             */
+    int64_t train_steps;    /* agent steps taken in training (each = same_action_num env steps)        */
     int64_t learn_iters;    /* DDQN.learn calls (self.it)                                              */
     int64_t test_steps;     /* real-env steps taken inside test() calls                                */
     double score;           /* statistics.mean(final test rewards) (agents/GTN_worker.py:209)          */
@@ -147,8 +147,8 @@ int le_rn_reward(const le_lane_cfg* cfg, const float* theta_dev /*[pop][P_rn]*/,
                  const float* state_dev, const float* next_state_dev, const float* real_reward_dev,
                  float* reward_dev, void* stream);
 
-/* Critic_DQN.forward (models/actor_critic.py:84-91) + greedy argmax (agents/DDQN.py:106-110):
- * one Q-net per lane (q_theta [n][P_q]), one state row per lane.                                      */
+/* Critic_DQN.forward / Critic_DuelingDQN.forward (models/actor_critic.py:84-122) + greedy argmax
+ * (agents/DDQN.py:106-110): one Q-net per lane (q_theta [n][P_q]), one state row per lane.            */
 int le_qnet_forward(const le_lane_cfg* cfg, const float* q_theta_dev, int n, const float* state_dev,
                     float* q_out_dev /*[n][ad]*/, int32_t* argmax_dev /*[n]*/, void* stream);
 
@@ -157,7 +157,8 @@ int le_real_env_step(int real_env, int max_steps, double* state_dev /*[n][4]*/, 
                      const int32_t* action_dev, float* obs_dev /*[n][sd]*/, float* reward_dev, float* done_dev,
                      int n, void* stream);
 
-/* DDQN.learn (agents/DDQN.py:60-95) on explicit minibatches: per lane B rows [s(sd) a s'(sd) r d] packed
+/* DDQN.learn (agents/DDQN.py:60-95) / DuelingDDQN.learn (agents/DuelingDDQN.py:59-94) on explicit minibatches:
+ * per lane B rows [s(sd) a s'(sd) r d] packed
  * (2*sd+3 floats).  Updates q_theta/q_target/m/v in place, t_dev[n] is Adam's step count, loss_dev[n] out. */
 int le_td_update(const le_lane_cfg* cfg, float* q_theta_dev, float* q_target_dev, float* adam_m_dev,
                  float* adam_v_dev, int32_t* adam_t_dev, int n, const float* batch_rows_dev /*[n][B][2sd+3]*/,
@@ -180,7 +181,9 @@ int le_inner_loop_plan(const le_lane_cfg* cfg, int n_lanes, int n_env, int* grid
  * Runs n_lanes complete `calc_score`s (agents/GTN_worker.py:187-221) — train() with ε-greedy acting
  * (agents/DDQN.py:97-104), SE/RN/real env step, replay append (utils.py:24-32), TD update
  * (agents/DDQN.py:60-95), per-episode greedy test() on the real env, early-out (agents/base_agent.py:49-62)
- * and the final test() — in ONE persistent kernel, one warp per lane.
+ * and the final test() — in ONE persistent kernel: one warp per lane for Critic_DQN with hidden_layer <= 1 and
+ * hidden_size <= 128 (weights in registers), one 256-thread CTA per lane for every other Q-net (DuelingDDQN,
+ * two hidden layers, wider nets).  Lanes of one launch must all fall into the same of the two families.
  *
  *   cfg_dev        [n_cfg] lane configurations (DEVICE); lane i uses cfg_dev[n_cfg == 1 ? 0 : i]  (vary_hp:
  *                  per-lane lr / batch_size / q_hidden <= cfg_host0->q_hidden).  cfg_host0 = HOST copy of the
