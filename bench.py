@@ -286,7 +286,7 @@ def run_vary_hp_workload(args):
     t0 = time.perf_counter()
     e2e_steps = 0
     for k in range(args.steps):
-        _, st, _, _ = vary_hp.evaluate_agents(d, theta_host.reshape(1, -1), n, seed=1000 + rank, overrides=over, device=dev)
+        _, st, _, _ = vary_hp.evaluate_agents(d, theta_host.reshape(1, -1), n, seed=1000 + rank, overrides=over, device=dev, shard=False)
         e2e_steps += sum(st[0])
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -51,21 +51,42 @@ def _max_cfg(cfgs):
     return m
 
 
+def _run_group(sub, cfg0, theta, env_index, keys, n_env, device):
+    """One launch of the fused kernel for lanes that share a kernel family.  Returns (final test rewards [k, T] f64,
+    training agent steps [k], episodes [k]) as numpy arrays.  (CPU tests substitute an oracle-backed version.)"""
+    bufs = ops.InnerLoopBuffers(cfg0, len(sub), max(n_env, 1), device, n_cfg=len(sub))
+    th = None if theta is None else torch.as_tensor(theta).to(device).contiguous()
+    ei = None if env_index is None else torch.as_tensor(env_index.astype(np.int32)).to(device)
+    ops.inner_loop_run(bufs, sub, th, ei, ops.keys_tensor(keys, device), cfg0=cfg0)
+    torch.cuda.current_stream().synchronize()
+    out = bufs.results()
+    return bufs.test_rewards.cpu().numpy(), out["train_steps"].astype(np.int64), out["n_episodes"].astype(np.int64)
+
+
+def _rank_world(shard):
+    import torch.distributed as dist
+    if shard and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def evaluate_agents(config, env_thetas, agents_num=10, seed=0, overrides=None, vary=True, env_slopes=None, device="cuda",
-                    env_kind=ENV_SE, n_envs=None):
+                    env_kind=ENV_SE, n_envs=None, shard=True):
     """`agents_num` freshly sampled agents on EACH of the given training environments, all lanes in one launch per
     kernel family (lane = env * agents_num + agent; lanes of one environment share its weight pack).
 
     env_thetas: [n_env, P] SE parameter vectors (ENV_SE), or None with env_kind=ENV_REAL and n_envs repetitions
     (mode 0 of experiments/syn_env_run_vary_hp.py:48-59: train on the real env itself).
+    With an initialised torch.distributed group (one process per GPU) and shard=True the lanes are block-sharded over the
+    ranks — every rank samples the same agent configurations from `seed`, runs lanes [n*rank/world, n*(rank+1)/world) and
+    the only exchange is ONE all-reduce that assembles the result table on every rank (BASELINE config 4).
     Returns (rewards [n_env][agents][test_episodes], train_steps [n_env][agents], episodes [n_env][agents], lane_cfgs)."""
     if env_thetas is None:
         n_env = int(n_envs or 1)
         theta = None
     else:
-        theta = torch.as_tensor(np.asarray(env_thetas, np.float32)).to(device)
-        theta = theta.reshape(1, -1) if theta.dim() == 1 else theta
-        theta = theta.contiguous()
+        theta = np.ascontiguousarray(np.asarray(env_thetas, np.float32))
+        theta = theta.reshape(1, -1) if theta.ndim == 1 else theta
         n_env = theta.shape[0]
     n = n_env * agents_num
     rng = np.random.RandomState(seed)
@@ -74,27 +95,34 @@ def evaluate_agents(config, env_thetas, agents_num=10, seed=0, overrides=None, v
         c.env_kind = env_kind
     env_of = np.arange(n) // agents_num
     keys = lane_keys(seed, 0, env_of, np.zeros(n, int), np.arange(n) % agents_num)
-    rewards = [None] * n
-    steps = [0] * n
-    episodes = [0] * n
+    rank, world = _rank_world(shard)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    T = max(c.test_episodes for c in cfgs)
+    table = np.zeros((n, T + 2), np.float64)      # [test rewards | train steps | episodes] per lane; zero outside this rank's block
     groups = {True: [], False: []}
-    for i, c in enumerate(cfgs):
-        groups[c.q_is_register_resident()].append(i)
+    for i in range(lo, hi):
+        groups[cfgs[i].q_is_register_resident()].append(i)
     for resident, idx in groups.items():
         if not idx:
             continue
+        idx = np.asarray(idx)
         sub = [cfgs[i] for i in idx]
-        cfg0 = _max_cfg(sub)
-        bufs = ops.InnerLoopBuffers(cfg0, len(idx), max(n_env, 1), device, n_cfg=len(idx))
-        env_index = None if theta is None or n_env == 1 else torch.as_tensor(env_of[idx].astype(np.int32)).to(device)
-        ops.inner_loop_run(bufs, sub, theta, env_index, ops.keys_tensor(keys[idx], device), cfg0=cfg0)
-        torch.cuda.current_stream().synchronize()
-        out = bufs.results()
-        tr = bufs.test_rewards.cpu().numpy()
+        env_index = None if theta is None or n_env == 1 else env_of[idx]
+        tr, st, ep = _run_group(sub, _max_cfg(sub), theta, env_index, keys[idx], n_env, device)
         for k, i in enumerate(idx):
-            rewards[i] = tr[k, :cfgs[i].test_episodes].tolist()
-            steps[i] = int(out["train_steps"][k]) * max(int(cfgs[i].same_action_num), 1)   # sum(episode_length)
-            episodes[i] = int(out["n_episodes"][k])
+            table[i, :cfgs[i].test_episodes] = tr[k, :cfgs[i].test_episodes]
+            table[i, T] = int(st[k]) * max(int(cfgs[i].same_action_num), 1)   # sum(episode_length)
+            table[i, T + 1] = int(ep[k])
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.from_numpy(table)
+        if dist.get_backend() == "nccl":
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)       # blocks are disjoint: the sum is the gather
+        table = t.cpu().numpy()
+    rewards = [table[i, :cfgs[i].test_episodes].tolist() for i in range(n)]
+    steps = [int(table[i, T]) for i in range(n)]
+    episodes = [int(table[i, T + 1]) for i in range(n)]
     nest = lambda v: [v[e * agents_num:(e + 1) * agents_num] for e in range(n_env)]
     return nest(rewards), nest(steps), nest(episodes), cfgs
 
@@ -200,7 +228,8 @@ def run_vary_hp(mode, experiment_name, model_num, agents_num, model_dir, custom_
         else:
             reward_list += r_i; train_steps_needed += s_i; episode_length_needed += e_i
         env_reward_overview[name] = {} if correlation_exp else np.hstack(r_i)
-    file_name = save_lists(mode=mode, config=config, reward_list=reward_list, train_steps_needed=train_steps_needed,
-                           episode_length_needed=episode_length_needed, env_reward_overview=env_reward_overview,
-                           experiment_name=experiment_name, out_dir=out_dir)
-    return file_name
+    if _rank_world(True)[0] != 0:      # sharded run: every rank holds the full result table, rank 0 writes it
+        return os.path.join(out_dir or os.getcwd(), str(mode) + '_' + (experiment_name or "_experiment_") + '.pt')
+    return save_lists(mode=mode, config=config, reward_list=reward_list, train_steps_needed=train_steps_needed,
+                      episode_length_needed=episode_length_needed, env_reward_overview=env_reward_overview,
+                      experiment_name=experiment_name, out_dir=out_dir)

@@ -243,3 +243,25 @@ def test_gtn_master_two_ranks_gloo_matches_single_rank(tmp_path, mode):
         assert np.array_equal(r0, single)
     else:
         assert np.allclose(r0, single, rtol=1e-5, atol=1e-7)
+
+
+def test_vary_hp_two_ranks_gloo_matches_single_rank(tmp_path):
+    """BASELINE config 4 sharding: world_size 2 over gloo, agents block-sharded (3 + 3 lanes), one all-reduce assembles
+    the result table: both ranks return the single-process result, each having run only its own block."""
+    import json
+    script = os.path.join(ROOT, "tests", "gloo_vary_hp_worker.py")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out1 = tmp_path / "single.json"
+    subprocess.check_call([sys.executable, script, "--out", str(out1)], env=env, cwd=str(tmp_path))
+    out2 = tmp_path / "dist"
+    port = 31000 + os.getpid() % 2000
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                           "127.0.0.1", "--master-port", str(port), script, "--out", str(out2)], env=env, cwd=str(tmp_path),
+                          timeout=600)
+    single = json.load(open(out1))
+    r0, r1 = json.load(open(str(out2) + ".rank0.json")), json.load(open(str(out2) + ".rank1.json"))
+    assert single["lanes_run_here"] == 6 and r0["lanes_run_here"] == 3 and r1["lanes_run_here"] == 3
+    for k in ("rewards", "steps", "episodes", "hidden"):
+        assert r0[k] == single[k] and r1[k] == single[k], k
+    assert len(single["rewards"]) == 2 and len(single["rewards"][0]) == 3 and len(single["rewards"][0][0]) == 2
+    assert len(set(single["hidden"])) > 2          # per-lane hyper-parameters really vary
