@@ -53,7 +53,7 @@ def _max_cfg(cfgs):
 
 def _run_group(sub, cfg0, theta, env_index, keys, n_env, device):
     """One launch of the fused kernel for lanes that share a kernel family.  Returns (final test rewards [k, T] f64,
-    training agent steps [k], episodes [k]) as numpy arrays.  (CPU tests substitute an oracle-backed version.)"""
+    training agent steps [k], episodes [k]) as numpy arrays.  (the CPU host-logic tests substitute their own launch function.)"""
     bufs = ops.InnerLoopBuffers(cfg0, len(sub), max(n_env, 1), device, n_cfg=len(sub))
     th = None if theta is None else torch.as_tensor(theta).to(device).contiguous()
     ei = None if env_index is None else torch.as_tensor(env_index.astype(np.int32)).to(device)
