@@ -122,8 +122,6 @@ def gen_td_update(yaml_name, tag, seed, steps=5, agent=None, **overrides):
     import torch
     mods = rh.import_reference()
     cfg, agent_name = small_config(yaml_name, agent, **overrides)
-    if env_overrides:
-        cfg["envs"][cfg["env_name"]].update(env_overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     real_env = fac.generate_real_env()
