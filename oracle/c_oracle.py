@@ -175,3 +175,29 @@ def run_lanes(cfgs, env_theta, env_index, keys, q_init_w=None, n_threads=1):
                 train_steps=np.array([o.train_steps for o in out]), learn_iters=np.array([o.learn_iters for o in out]),
                 test_steps=np.array([o.test_steps for o in out]), score=np.array([o.score for o in out]),
                 rewards=rewards, lengths=lengths, test_rewards=test_rewards, q_final=qf)
+
+
+def td3_learn(dims, hyper, nets, adam, counters, total_it, rows, policy_noise, expo_target, expo_actor, gumbel_tau):
+    """TD3_discrete_vary.learn restatement, in place on the float32 arrays in `nets` (actor, actor_target, critic_1,
+    critic_target_1, critic_2, critic_target_2) and `adam` (m_a, v_a, m_c1, v_c1, m_c2, v_c2).
+    dims = (sd, ad, H, L, act); hyper = dict(gamma, tau, lr, policy_delay, max_action, policy_std, policy_std_clip, gumbel_hard);
+    counters = [t_actor, t_critic] (updated).  Returns (critic_loss, actor_loss or nan)."""
+    L = lib()
+    L.le_oracle_td3_learn.restype = C.c_float
+    sd, ad, H, nl, act = dims
+    ta, tc = C.c_int32(counters[0]), C.c_int32(counters[1])
+    al = C.c_float()
+    rows = np.ascontiguousarray(rows, np.float32)
+    args = [np.ascontiguousarray(a, np.float32) for a in (policy_noise, expo_target, expo_actor)]
+    for a in list(nets.values()) + list(adam.values()):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+    loss = L.le_oracle_td3_learn(
+        C.c_int(sd), C.c_int(ad), C.c_int(H), C.c_int(nl), C.c_int(act), C.c_double(hyper["gamma"]), C.c_double(hyper["tau"]),
+        C.c_double(hyper["lr"]), C.c_int(hyper["policy_delay"]), C.c_float(hyper["max_action"]), C.c_float(hyper["policy_std"]),
+        C.c_float(hyper["policy_std_clip"]), C.c_float(gumbel_tau), C.c_int(hyper["gumbel_hard"]),
+        _p(nets["actor"]), _p(nets["actor_target"]), _p(nets["critic_1"]), _p(nets["critic_target_1"]), _p(nets["critic_2"]),
+        _p(nets["critic_target_2"]), _p(adam["m_a"]), _p(adam["v_a"]), _p(adam["m_c1"]), _p(adam["v_c1"]), _p(adam["m_c2"]),
+        _p(adam["v_c2"]), C.byref(ta), C.byref(tc), C.c_int(total_it), _p(rows), C.c_int(rows.shape[0]), _p(args[0]), _p(args[1]),
+        _p(args[2]), C.byref(al))
+    counters[0], counters[1] = ta.value, tc.value
+    return float(loss), float(al.value)

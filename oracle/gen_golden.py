@@ -160,6 +160,81 @@ def gen_td_update(yaml_name, tag, seed, steps=5, agent=None, **overrides):
              cfg=cfg_bytes(cfg, agent_name, ENV_RN if "reward_env" in yaml_name else ENV_SE))
 
 
+def gen_td3_learn(seed, steps=5):
+    """TD3_discrete_vary.learn (agents/TD3_discrete_vary.py:62-119) `steps` times on explicit minibatches with the random
+    draws (policy noise randn_like, the exponential_() of both gumbel_softmax calls) logged: groundwork for SURVEY §8(f) rank 2."""
+    import torch
+    mods = rh.import_reference()
+    cfg, agent_name = small_config("default_config_cartpole_syn_env.yaml", "td3_discrete_vary", hidden_size=24, hidden_layer=2,
+                                   batch_size=16, policy_delay=2, vary_hp=False)
+    torch.manual_seed(seed)
+    agent = mods["agents.agent_utils"].select_agent(cfg, "td3_discrete_vary")
+    sd, ad, B = agent.state_dim, agent.action_dim, agent.batch_size
+    rng = np.random.RandomState(seed)
+    ROW = 2 * sd + ad + 2
+    rows = np.zeros((steps, B, ROW), np.float32)
+    rows[:, :, :sd] = rng.uniform(-1, 1, size=(steps, B, sd))
+    onehot = np.eye(ad, dtype=np.float32)[rng.randint(0, ad, size=(steps, B))]
+    rows[:, :, sd:sd + ad] = onehot + rng.standard_normal((steps, B, ad)).astype(np.float32) * 0.04
+    rows[:, :, sd + ad:2 * sd + ad] = rng.uniform(-1, 1, size=(steps, B, sd))
+    rows[:, :, 2 * sd + ad] = rng.uniform(-1, 1, size=(steps, B))
+    rows[:, :, 2 * sd + ad + 1] = (rng.uniform(size=(steps, B)) < 0.1) * 1.0
+
+    class FakeRB(object):
+        k = 0
+
+        def sample(self, batch_size):
+            r = torch.from_numpy(rows[FakeRB.k])
+            FakeRB.k += 1
+            return (r[:, :sd], r[:, sd:sd + ad], r[:, sd + ad:2 * sd + ad], r[:, 2 * sd + ad:2 * sd + ad + 1], r[:, 2 * sd + ad + 1:])
+
+    log = {"randn": [], "expo": []}
+    orig_randn_like, orig_expo = torch.randn_like, torch.Tensor.exponential_
+
+    def fake_randn_like(t, **kw):
+        v = torch.from_numpy(rng.standard_normal(tuple(t.shape)).astype(np.float32))
+        log["randn"].append(v.numpy().copy())
+        return v
+
+    def fake_exponential_(self, lambd=1.0, generator=None):
+        v = torch.from_numpy(rng.exponential(size=tuple(self.shape)).astype(np.float32))
+        log["expo"].append(v.numpy().copy())
+        with torch.no_grad():
+            self.copy_(v)
+        return self
+
+    nets = ("actor", "actor_target", "critic_1", "critic_target_1", "critic_2", "critic_target_2")
+    init = {n: linear_params(getattr(agent, n)) for n in nets}
+    per_step = {n: [] for n in nets}
+    temps, updated, n_expo = [], [], []
+    torch.randn_like, torch.Tensor.exponential_ = fake_randn_like, fake_exponential_
+    try:
+        rb = FakeRB()
+        for k in range(steps):
+            before = len(log["expo"])
+            agent.learn(replay_buffer=rb, env=None, episode=10)
+            temps.append(float(agent.gumbel_temp_annealed))
+            n_expo.append(len(log["expo"]) - before)
+            updated.append(int(agent.total_it % agent.policy_delay == 0))
+            for n in nets:
+                per_step[n].append(linear_params(getattr(agent, n)))
+    finally:
+        torch.randn_like, torch.Tensor.exponential_ = orig_randn_like, orig_expo
+    assert n_expo == [1 + u for u in updated], n_expo
+    expo_target, expo_actor, i = [], [], 0
+    for u in updated:
+        expo_target.append(log["expo"][i]); i += 1
+        expo_actor.append(log["expo"][i] if u else np.zeros((B, ad), np.float32)); i += u
+    a = cfg["agents"]["td3_discrete_vary"]
+    np.savez(os.path.join(GOLDEN, "td3_learn_cartpole.npz"), sd=sd, ad=ad, hidden=a["hidden_size"], layers=a["hidden_layer"],
+             gamma=a["gamma"], tau=a["tau"], lr=a["lr"], policy_delay=a["policy_delay"], policy_std=a["policy_std"],
+             policy_std_clip=a["policy_std_clip"], gumbel_hard=int(a["gumbel_softmax_hard"]), max_action=float(agent.max_action),
+             temps=np.array(temps, np.float64), updated=np.array(updated, np.int32), rows=rows, policy_noise=np.stack(log["randn"]),
+             expo_target=np.stack(expo_target), expo_actor=np.stack(expo_actor),
+             **{"init_" + n: init[n] for n in nets}, **{"after_" + n: np.stack(per_step[n]) for n in nets})
+    print("td3_learn: steps", steps, "policy updates", updated, "temps", temps[:2])
+
+
 def gen_real_env(seed):
     """Trajectories of the gym stand-in (oracle/stubs/gym) — pins the C/CUDA dynamics to the restated equations."""
     import gym
@@ -344,6 +419,7 @@ def main():
         ("td_update_cartpole_dueling", lambda: gen_td_update(CP, "cartpole_dueling", 8, agent="DuelingDDQN")),
         ("td_update_acrobot_dueling", lambda: gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")),
         ("td_update_cartpole_ddqn_l2", lambda: gen_td_update(CP, "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)),
+        ("td3_learn_cartpole", lambda: gen_td3_learn(41)),
         ("real_env", lambda: gen_real_env(7)),
         ("trajectory_cartpole_se", lambda: gen_trajectory(CP, "cartpole_se", 11, (0x1234, 0xABCD), "se",
                                                           dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)),

@@ -308,6 +308,160 @@ static float td_update_general(const le_lane_cfg* c, float* th, float* thT, floa
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* TD3_discrete_vary.learn (agents/TD3_discrete_vary.py:62-119) — groundwork for the next row of SURVEY.md §8(f):
+ * actor = Actor_TD3_discrete (models/actor_critic.py:22-36: MLP * max_action -> F.gumbel_softmax), two Critic_Q
+ * (:69-76: MLP over cat(state, action)), three target nets, two Adam optimizers, delayed policy update.  Randomness
+ * (policy noise, Gumbel noise) is an INPUT, so the restatement is independent of any stream definition. */
+
+typedef struct { int nl; olayer l[4]; int P, S, in, out; } omlp;
+
+static void build_mlp(omlp* n, int in, int H, int L, int out, int act) {
+    int p = 0, y = 0;
+    n->nl = 0; n->in = in; n->out = out;
+    add_layer(&n->l[n->nl++], in, H, act, &p, &y);
+    for (int i = 1; i < (L > 1 ? L : 1); ++i) add_layer(&n->l[n->nl++], H, H, act, &p, &y);
+    add_layer(&n->l[n->nl++], H, out, LE_ACT_IDENTITY, &p, &y);
+    n->P = p; n->S = y;
+}
+static const float* mlp_fwd_row(const omlp* n, const float* th, const float* x, float* acts) {
+    const float* in = x;
+    for (int i = 0; i < n->nl; ++i) { layer_fwd(&n->l[i], th, in, acts + n->l[i].y_off); in = acts + n->l[i].y_off; }
+    return in;
+}
+/* backward of one row: d = gradient record (same offsets as acts, destroyed), dx_in (may be NULL) receives dL/dx */
+static void mlp_bwd_row(const omlp* n, const float* th, float* g, const float* x, const float* acts, float* d, float* dx_in) {
+    for (int i = n->nl - 1; i >= 0; --i) {
+        const olayer* l = &n->l[i];
+        layer_bwd(l, th, g, i > 0 ? acts + n->l[i - 1].y_off : x, acts + l->y_off, d + l->y_off, i > 0 ? d + n->l[i - 1].y_off : dx_in);
+    }
+}
+/* F.gumbel_softmax(logits, tau, hard) for one row; expo = the Exp(1) samples torch draws (gumbel = -log(expo)) */
+static void gumbel_softmax_row(const float* logits, const float* expo, int n, float tau, int hard, float* y_soft, float* ret) {
+    float z[LE_ORACLE_MAX_AD], mx = -INFINITY, sum = 0.f;
+    for (int k = 0; k < n; ++k) { z[k] = (logits[k] + (-logf(expo[k]))) / tau; if (z[k] > mx) mx = z[k]; }
+    for (int k = 0; k < n; ++k) { y_soft[k] = expf(z[k] - mx); sum += y_soft[k]; }
+    for (int k = 0; k < n; ++k) y_soft[k] = y_soft[k] / sum;
+    if (!hard) { for (int k = 0; k < n; ++k) ret[k] = y_soft[k]; return; }
+    int idx = 0;
+    for (int k = 1; k < n; ++k) if (y_soft[k] > y_soft[idx]) idx = k;
+    for (int k = 0; k < n; ++k) ret[k] = ((k == idx ? 1.f : 0.f) - y_soft[k]) + y_soft[k];   /* y_hard - y_soft.detach() + y_soft */
+}
+static void adam_vec(float* th, float* m, float* v, const float* g, int P, int t, double lr, double b1d, double b2d, double epsd) {
+    const float w1 = (float)(1.0 - b1d), b2f = (float)b2d, w2 = (float)(1.0 - b2d);
+    const double bc1 = 1.0 - pow(b1d, (double)t), bc2 = 1.0 - pow(b2d, (double)t);
+    const float neg_step = (float)(-(lr / bc1)), bc2s = (float)sqrt(bc2), epsf = (float)epsd;
+    for (int p = 0; p < P; ++p) {
+        m[p] = m[p] + w1 * (g[p] - m[p]);
+        v[p] = v[p] * b2f;
+        v[p] = v[p] + w2 * g[p] * g[p];
+        th[p] = th[p] + neg_step * m[p] / (sqrtf(v[p]) / bc2s + epsf);
+    }
+}
+
+int le_oracle_td3_params(int sd, int ad, int H, int L, int* P_actor, int* P_critic) {
+    omlp a, c; build_mlp(&a, sd, H, L, ad, LE_ACT_TANH); build_mlp(&c, sd + ad, H, L, 1, LE_ACT_TANH);
+    *P_actor = a.P; *P_critic = c.P;
+    return 0;
+}
+
+/* One learn() call.  rows [B][sd + ad + sd + 2] = [s | action vector | s' | r | d]; policy_noise [B][ad] = randn_like(actions);
+ * expo_target [B][ad], expo_actor [B][ad] = the exponential_() draws of the two gumbel_softmax calls (expo_actor is only read
+ * when this call updates the policy).  total_it is self.total_it AFTER the increment (1 on the first call).
+ * Returns the critic loss; *actor_loss is set when the policy was updated (else NaN). */
+float le_oracle_td3_learn(int sd, int ad, int H, int L, int act, double gamma, double tau, double lr, int policy_delay,
+                          float max_action, float policy_std, float policy_std_clip, float gumbel_tau, int gumbel_hard,
+                          float* actor, float* actorT, float* c1, float* c1T, float* c2, float* c2T,
+                          float* m_a, float* v_a, float* m_c1, float* v_c1, float* m_c2, float* v_c2, int32_t* t_actor, int32_t* t_critic,
+                          int total_it, const float* rows, int B, const float* policy_noise, const float* expo_target,
+                          const float* expo_actor, float* actor_loss) {
+    omlp na, nc; build_mlp(&na, sd, H, L, ad, act); build_mlp(&nc, sd + ad, H, L, 1, act);
+    const int ROW = 2 * sd + ad + 2, XI = sd + ad;
+    float* acts_a = (float*)malloc(sizeof(float) * na.S);
+    float* acts_c1 = (float*)malloc(sizeof(float) * (size_t)B * nc.S);
+    float* acts_c2 = (float*)malloc(sizeof(float) * (size_t)B * nc.S);
+    float* acts_t = (float*)malloc(sizeof(float) * nc.S);
+    float* tq = (float*)malloc(sizeof(float) * B);
+    float* g1 = (float*)calloc(nc.P, sizeof(float));
+    float* g2 = (float*)calloc(nc.P, sizeof(float));
+    float* d = (float*)malloc(sizeof(float) * (nc.S > na.S ? nc.S : na.S));
+    float x[LE_ORACLE_MAX_SD + LE_ORACLE_MAX_AD], ysoft[LE_ORACLE_MAX_AD], na_[LE_ORACLE_MAX_AD];
+    /* with torch.no_grad(): target actions and target Q (:73-83) */
+    for (int b = 0; b < B; ++b) {
+        const float* r = rows + (size_t)b * ROW;
+        const float* s2 = r + sd + ad;
+        const float* out = mlp_fwd_row(&na, actorT, s2, acts_a);
+        float logits[LE_ORACLE_MAX_AD];
+        for (int k = 0; k < ad; ++k) logits[k] = out[k] * max_action;
+        gumbel_softmax_row(logits, expo_target + (size_t)b * ad, ad, gumbel_tau, gumbel_hard, ysoft, na_);
+        for (int k = 0; k < ad; ++k) {
+            float nz = policy_noise[(size_t)b * ad + k] * policy_std;
+            nz = nz < -policy_std_clip ? -policy_std_clip : (nz > policy_std_clip ? policy_std_clip : nz);
+            x[sd + k] = na_[k] + nz;
+        }
+        memcpy(x, s2, sizeof(float) * sd);
+        const float q1 = *mlp_fwd_row(&nc, c1T, x, acts_t);
+        const float q2 = *mlp_fwd_row(&nc, c2T, x, acts_t);
+        const float mn = q1 < q2 ? q1 : q2;                                /* torch.min */
+        tq[b] = r[2 * sd + ad] + ((1.f - r[2 * sd + ad + 1]) * (float)gamma) * mn;   /* rewards + (1 - dones) * gamma * target_Q */
+    }
+    /* critic loss = mse(Q1, target) + mse(Q2, target); one Adam over both critics (:86-95) */
+    float l1 = 0.f, l2 = 0.f;
+    const float norm = (float)(2.0 / (double)B);
+    for (int b = 0; b < B; ++b) {
+        const float* r = rows + (size_t)b * ROW;     /* cat(state, action) is the first sd+ad entries of the row */
+        const float q1 = *mlp_fwd_row(&nc, c1, r, acts_c1 + (size_t)b * nc.S);
+        const float q2 = *mlp_fwd_row(&nc, c2, r, acts_c2 + (size_t)b * nc.S);
+        const float e1 = q1 - tq[b], e2 = q2 - tq[b];
+        l1 += e1 * e1; l2 += e2 * e2;
+        memset(d, 0, sizeof(float) * nc.S); d[nc.l[nc.nl - 1].y_off] = norm * e1;
+        mlp_bwd_row(&nc, c1, g1, r, acts_c1 + (size_t)b * nc.S, d, NULL);
+        memset(d, 0, sizeof(float) * nc.S); d[nc.l[nc.nl - 1].y_off] = norm * e2;
+        mlp_bwd_row(&nc, c2, g2, r, acts_c2 + (size_t)b * nc.S, d, NULL);
+    }
+    const float critic_loss = l1 / (float)B + l2 / (float)B;
+    *t_critic += 1;
+    adam_vec(c1, m_c1, v_c1, g1, nc.P, *t_critic, lr, 0.9, 0.999, 1e-8);
+    adam_vec(c2, m_c2, v_c2, g2, nc.P, *t_critic, lr, 0.9, 0.999, 1e-8);
+    *actor_loss = NAN;
+    if (total_it % policy_delay == 0) {   /* delayed policy update (:98-119) */
+        float* ga = (float*)calloc(na.P, sizeof(float));
+        float* gdummy = (float*)calloc(nc.P, sizeof(float));
+        float* da = (float*)malloc(sizeof(float) * na.S);
+        float lsum = 0.f;
+        for (int b = 0; b < B; ++b) {
+            const float* r = rows + (size_t)b * ROW;
+            const float* out = mlp_fwd_row(&na, actor, r, acts_a);
+            float logits[LE_ORACLE_MAX_AD], ret[LE_ORACLE_MAX_AD], dx[LE_ORACLE_MAX_SD + LE_ORACLE_MAX_AD];
+            for (int k = 0; k < ad; ++k) logits[k] = out[k] * max_action;
+            gumbel_softmax_row(logits, expo_actor + (size_t)b * ad, ad, gumbel_tau, gumbel_hard, ysoft, ret);
+            memcpy(x, r, sizeof(float) * sd);
+            for (int k = 0; k < ad; ++k) x[sd + k] = ret[k];
+            const float q = *mlp_fwd_row(&nc, c1, x, acts_t);          /* the critic AFTER its Adam step */
+            lsum += -q;
+            memset(d, 0, sizeof(float) * nc.S); d[nc.l[nc.nl - 1].y_off] = -1.f / (float)B;
+            memset(dx, 0, sizeof(dx));
+            mlp_bwd_row(&nc, c1, gdummy, x, acts_t, d, dx);             /* only dL/d(action) is used: the critic is not stepped */
+            /* straight-through: dL/dy_soft = dL/dret; softmax backward; / tau; * max_action */
+            float dot = 0.f;
+            for (int k = 0; k < ad; ++k) dot += ysoft[k] * dx[sd + k];
+            memset(da, 0, sizeof(float) * na.S);
+            for (int k = 0; k < ad; ++k) da[na.l[na.nl - 1].y_off + k] = (ysoft[k] * (dx[sd + k] - dot) / gumbel_tau) * max_action;
+            mlp_bwd_row(&na, actor, ga, r, acts_a, da, NULL);
+            (void)XI;
+        }
+        *actor_loss = lsum / (float)B;
+        *t_actor += 1;
+        adam_vec(actor, m_a, v_a, ga, na.P, *t_actor, lr, 0.9, 0.999, 1e-8);
+        const float tf = (float)tau, omt = (float)(1.0 - tau);
+        for (int p = 0; p < nc.P; ++p) { c1T[p] = tf * c1[p] + omt * c1T[p]; c2T[p] = tf * c2[p] + omt * c2T[p]; }
+        for (int p = 0; p < na.P; ++p) actorT[p] = tf * actor[p] + omt * actorT[p];
+        free(ga); free(gdummy); free(da);
+    }
+    free(acts_a); free(acts_c1); free(acts_c2); free(acts_t); free(tq); free(g1); free(g2); free(d);
+    return critic_loss;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* gym 0.17.3 classic_control (third-party, restated)                             */
 
 void le_oracle_cartpole_step(double st[4], int action, double* reward, int* done) {

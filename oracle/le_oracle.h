@@ -42,4 +42,13 @@ int le_oracle_run_lanes(const le_lane_cfg* cfgs, int n_cfg, const float* env_the
                         const uint32_t* keys, const float* q_init, float* q_final, int n_lanes, le_lane_out* out,
                         double* rewards, int32_t* lengths, double* test_rewards, int n_threads);
 int le_oracle_sizeof_cfg(void);
+/* TD3_discrete_vary.learn restatement (agents/TD3_discrete_vary.py:62-119): see le_oracle.c */
+int le_oracle_td3_params(int sd, int ad, int H, int L, int* P_actor, int* P_critic);
+float le_oracle_td3_learn(int sd, int ad, int H, int L, int act, double gamma, double tau, double lr, int policy_delay,
+                          float max_action, float policy_std, float policy_std_clip, float gumbel_tau, int gumbel_hard,
+                          float* actor, float* actorT, float* c1, float* c1T, float* c2, float* c2T,
+                          float* m_a, float* v_a, float* m_c1, float* v_c1, float* m_c2, float* v_c2, int32_t* t_actor, int32_t* t_critic,
+                          int total_it, const float* rows, int B, const float* policy_noise, const float* expo_target,
+                          const float* expo_actor, float* actor_loss);
+
 #endif
