@@ -201,3 +201,41 @@ def td3_learn(dims, hyper, nets, adam, counters, total_it, rows, policy_noise, e
         _p(args[2]), C.byref(al))
     counters[0], counters[1] = ta.value, tc.value
     return float(loss), float(al.value)
+
+
+class Td3Cfg(C.Structure):
+    """struct le_oracle_td3_cfg (oracle/le_oracle.h)."""
+    _fields_ = [("base", LaneCfg), ("policy_delay", C.c_int32), ("gumbel_hard", C.c_int32), ("action_std", C.c_double),
+                ("policy_std", C.c_double), ("policy_std_clip", C.c_double), ("gumbel_temp", C.c_double), ("max_action", C.c_double)]
+
+
+def td3_cfg(base, agent_cfg, max_action=1.0):
+    """base: LaneCfg with the env / loop fields; agent_cfg: the reference's config['agents']['td3_discrete_vary'] dict."""
+    t = Td3Cfg()
+    C.memmove(C.byref(t.base), C.byref(base), C.sizeof(LaneCfg))
+    t.policy_delay, t.gumbel_hard = int(agent_cfg["policy_delay"]), int(bool(agent_cfg["gumbel_softmax_hard"]))
+    t.action_std, t.policy_std, t.policy_std_clip = float(agent_cfg["action_std"]), float(agent_cfg["policy_std"]), float(agent_cfg["policy_std_clip"])
+    t.gumbel_temp, t.max_action = float(agent_cfg["gumbel_softmax_temp"]), float(max_action)
+    return t
+
+
+def run_lane_td3(tcfg, env_theta, key, actor_init, c1_init, c2_init, trace_cap=0):
+    """One TD3_discrete_vary calc_score-style lane (train with per-episode test + final test) on the CPU restatement."""
+    cfg = tcfg.base
+    env_theta = None if env_theta is None else np.ascontiguousarray(env_theta, np.float32)
+    a0, q1, q2 = [np.ascontiguousarray(x, np.float32) for x in (actor_init, c1_init, c2_init)]
+    af = np.zeros_like(a0)
+    out = LaneOut()
+    rewards = np.zeros(max(cfg.train_episodes, 1), np.float64)
+    lengths = np.zeros(max(cfg.train_episodes, 1), np.int32)
+    test_rewards = np.zeros(max(cfg.test_episodes, 1), np.float64)
+    tb = TraceBuf(trace_cap, cfg.sd) if trace_cap > 0 else None
+    ts = tb.struct() if tb else None
+    rc = lib().le_oracle_run_lane_td3(C.byref(tcfg), _p(env_theta), C.c_uint32(key[0]), C.c_uint32(key[1]), _p(a0), _p(q1), _p(q2), _p(af),
+                                      C.byref(out), _p(rewards), _p(lengths), _p(test_rewards), C.byref(ts) if ts is not None else None)
+    if rc != 0:
+        raise RuntimeError("le_oracle_run_lane_td3 failed: %d" % rc)
+    n = out.n_episodes
+    return dict(n_episodes=n, timed_out=out.timed_out, train_steps=out.train_steps, learn_iters=out.learn_iters, test_steps=out.test_steps,
+                score=out.score, rewards=rewards[:n].copy(), lengths=lengths[:n].copy(),
+                test_rewards=test_rewards[:cfg.test_episodes].copy(), actor_final=af, trace=tb)

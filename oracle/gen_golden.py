@@ -342,6 +342,63 @@ def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, us
           rewards[:4], "test", test_rewards[:3])
 
 
+def gen_trajectory_td3(tag, seed, key, overrides, trace_cap):
+    """BaseAgent.train (+ per-episode test) and test of the reference's TD3_discrete_vary on a CartPole SE under RNG injection
+    (oracle/ref_harness.py Td3RngInjector): groundwork for SURVEY §8(f) rank 2."""
+    import torch
+    mods = rh.import_reference()
+    yaml_name = "default_config_cartpole_syn_env.yaml"
+    cfg, agent_name = small_config(yaml_name, "td3_discrete_vary", **overrides)
+    torch.manual_seed(seed)
+    fac = mods["envs.env_factory"].EnvFactory(cfg)
+    real_env = fac.generate_real_env()
+    train_env = fac.generate_virtual_env()
+    env_theta = linear_params(train_env)
+    agent = mods["agents.agent_utils"].select_agent(cfg, "td3_discrete_vary")
+    init = {n: linear_params(getattr(agent, n)) for n in ("actor", "critic_1", "critic_2")}
+    inj = rh.Td3RngInjector(key, agent.action_dim, "cartpole")
+    tr = dict(action=[], next_state=[], reward=[], done=[])
+    orig_step = train_env.step
+
+    def step(action, state=None):
+        s2, r, d = orig_step(action=action) if state is None else orig_step(action=action, state=state)
+        tr["action"].append(int(action.reshape(-1)[0].item()))
+        tr["next_state"].append(s2.detach().numpy().astype(np.float32).copy())
+        tr["reward"].append(float(r))
+        tr["done"].append(float(d))
+        return s2, r, d
+
+    train_env.step = step
+    with rh.injected_rng_td3(inj, agent, reset_envs=[train_env.env.reset_env.env.unwrapped, real_env.env.unwrapped],
+                             action_spaces=[train_env.env.action_space]):
+        rewards, lengths, _ = agent.train(env=train_env, test_env=real_env)
+        test_rewards, _, _ = agent.test(env=real_env)
+    n = min(trace_cap, len(tr["action"]))
+    a = cfg["agents"]["td3_discrete_vary"]
+    np.savez(os.path.join(GOLDEN, "trajectory_td3_%s.npz" % tag), key=np.array(key, np.uint32),
+             cfg=cfg_bytes_td3(cfg), agent_cfg_json=np.array(__import__("json").dumps(a)), max_action=float(agent.max_action),
+             env_theta=env_theta, init_actor=init["actor"], init_critic_1=init["critic_1"], init_critic_2=init["critic_2"],
+             actor_final=linear_params(agent.actor), rewards=np.array(rewards, np.float64), lengths=np.array(lengths, np.int32),
+             test_rewards=np.array(test_rewards, np.float64), train_steps=len(tr["action"]), learn_iters=inj.learn_iters,
+             action=np.array(tr["action"][:n], np.int32), next_state=np.stack(tr["next_state"][:n]),
+             reward=np.array(tr["reward"][:n], np.float32), done=np.array(tr["done"][:n], np.float32))
+    print("trajectory_td3", tag, "episodes", len(rewards), "steps", len(tr["action"]), "learn", inj.learn_iters, "rewards", rewards[:4],
+          "test", test_rewards[:3])
+
+
+def cfg_bytes_td3(cfg):
+    """le_lane_cfg bytes for a TD3 lane: env / loop fields from the ddqn-style mapping, MLP shape from the td3 section."""
+    d = copy.deepcopy(cfg)
+    a = d["agents"]["td3_discrete_vary"]
+    ddqn_like = dict(d["agents"]["ddqn"])
+    for k in ("train_episodes", "test_episodes", "init_episodes", "batch_size", "gamma", "lr", "tau", "rb_size", "same_action_num",
+              "activation_fn", "hidden_size", "hidden_layer", "early_out_num", "early_out_virtual_diff"):
+        ddqn_like[k] = a[k]
+    d["agents"]["ddqn"] = ddqn_like
+    c = le_config.lane_cfg(d, agent_name="ddqn", env_kind=ENV_SE, use_test_env=True, final_test=True)
+    return np.frombuffer(bytes(c), dtype=np.uint8).copy()
+
+
 def gen_nes(seed):
     """GTN_Master.score_transform (agents/GTN_master.py:197-265) for all 8 types, and update_env (:267-298)."""
     import torch
@@ -420,6 +477,10 @@ def main():
         ("td_update_acrobot_dueling", lambda: gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")),
         ("td_update_cartpole_ddqn_l2", lambda: gen_td_update(CP, "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)),
         ("td3_learn_cartpole", lambda: gen_td3_learn(41)),
+        ("trajectory_td3_cartpole_se", lambda: gen_trajectory_td3("cartpole_se", 42, (0x81, 0x82),
+                                                                  dict(train_episodes=4, test_episodes=2, init_episodes=1, hidden_size=24,
+                                                                       hidden_layer=2, batch_size=16, policy_delay=2, vary_hp=False),
+                                                                  trace_cap=400)),
         ("real_env", lambda: gen_real_env(7)),
         ("trajectory_cartpole_se", lambda: gen_trajectory(CP, "cartpole_se", 11, (0x1234, 0xABCD), "se",
                                                           dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)),

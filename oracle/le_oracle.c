@@ -807,6 +807,186 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* TD3_discrete_vary lane: BaseAgent.train / test (agents/base_agent.py:64-227) with select_train_action / select_test_action
+ * (agents/TD3_discrete_vary.py:155-166) and learn (:62-119).  Streams: oracle/philox.py P_TD3_EXPO / P_TD3_NORMAL. */
+void le_oracle_td3_expo(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out) {
+    for (int i = 0; i < n; i += 4) {
+        uint32_t w[4];
+        le_oracle_philox(c0, phase, LE_P_TD3_EXPO, (uint32_t)(i >> 2), k0, k1, w);
+        for (int k = 0; k < 4 && i + k < n; ++k) out[i + k] = (float)(-log(((double)w[k] + 0.5) * (1.0 / 4294967296.0)));
+    }
+}
+void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out) {
+    for (int i = 0; i < n; i += 4) {
+        uint32_t w[4];
+        le_oracle_philox(c0, phase, LE_P_TD3_NORMAL, (uint32_t)(i >> 2), k0, k1, w);
+        double z[4];
+        for (int h = 0; h < 2; ++h) {
+            const double u1 = ((double)w[2 * h] + 1.0) * (1.0 / 4294967296.0), u2 = (double)w[2 * h + 1] * (1.0 / 4294967296.0);
+            const double r = sqrt(-2.0 * log(u1)), t = (2.0 * M_PI) * u2;
+            z[2 * h] = r * cos(t); z[2 * h + 1] = r * sin(t);
+        }
+        for (int k = 0; k < 4 && i + k < n; ++k) out[i + k] = (float)z[k];
+    }
+}
+
+/* actor(state, temp) + randn(ad) * action_std -> action vector; returns its argmax (first maximum) */
+static int td3_act(const le_oracle_td3_cfg* tc, const omlp* na, const float* actor, float* acts, const float* state, float temp,
+                   uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, float* avec) {
+    const int ad = tc->base.ad;
+    float logits[LE_ORACLE_MAX_AD] = {0}, expo[LE_ORACLE_MAX_AD], nz[LE_ORACLE_MAX_AD], ysoft[LE_ORACLE_MAX_AD], ret[LE_ORACLE_MAX_AD];
+    const float* o = mlp_fwd_row(na, actor, state, acts);
+    for (int k = 0; k < ad; ++k) logits[k] = o[k] * (float)tc->max_action;
+    le_oracle_td3_expo(k0, k1, phase, c0, ad, expo);
+    le_oracle_td3_normal(k0, k1, phase, c0, ad, nz);
+    gumbel_softmax_row(logits, expo, ad, temp, tc->gumbel_hard, ysoft, ret);
+    int best = 0;
+    for (int k = 0; k < ad; ++k) { avec[k] = ret[k] + nz[k] * (float)tc->action_std; if (avec[k] > avec[best]) best = k; }
+    return best;
+}
+
+int le_oracle_run_lane_td3(const le_oracle_td3_cfg* tc, const float* env_theta, uint32_t k0, uint32_t k1, const float* actor_init,
+                           const float* c1_init, const float* c2_init, float* actor_final, le_lane_out* out, double* rewards,
+                           int32_t* lengths, double* test_rewards, const le_trace* tr) {
+    const le_lane_cfg* c = &tc->base;
+    if (c->sd > LE_ORACLE_MAX_SD || c->ad > LE_ORACLE_MAX_AD) return -1;
+    const int sd = c->sd, ad = c->ad, H = c->q_hidden, L = c->q_layers > 1 ? c->q_layers : 1, B = c->batch_size;
+    const int ROW = 2 * sd + ad + 2, K = c->same_action_num > 1 ? c->same_action_num : 1;
+    omlp na, nc; build_mlp(&na, sd, H, L, ad, c->q_act); build_mlp(&nc, sd + ad, H, L, 1, c->q_act);
+    float* nets = (float*)calloc((size_t)2 * na.P + 4 * nc.P, sizeof(float));
+    float *actor = nets, *actorT = actor + na.P, *c1 = actorT + na.P, *c1T = c1 + nc.P, *c2 = c1T + nc.P, *c2T = c2 + nc.P;
+    memcpy(actor, actor_init, sizeof(float) * na.P); memcpy(actorT, actor_init, sizeof(float) * na.P);
+    memcpy(c1, c1_init, sizeof(float) * nc.P); memcpy(c1T, c1_init, sizeof(float) * nc.P);
+    memcpy(c2, c2_init, sizeof(float) * nc.P); memcpy(c2T, c2_init, sizeof(float) * nc.P);
+    float* mom = (float*)calloc((size_t)2 * na.P + 4 * nc.P, sizeof(float));
+    float *m_a = mom, *v_a = m_a + na.P, *m_c1 = v_a + na.P, *v_c1 = m_c1 + nc.P, *m_c2 = v_c1 + nc.P, *v_c2 = m_c2 + nc.P;
+    int32_t t_actor = 0, t_critic = 0;
+    int64_t max_total = (int64_t)c->train_episodes * c->max_steps;
+    if (c->step_budget > 0 && c->step_budget + c->max_steps < max_total) max_total = c->step_budget + c->max_steps;
+    int rb_cap = c->rb_size < max_total ? c->rb_size : (int)max_total; if (rb_cap < 1) rb_cap = 1;
+    float* rb = (float*)malloc(sizeof(float) * (size_t)rb_cap * ROW);
+    float* batch = (float*)malloc(sizeof(float) * (size_t)B * ROW);
+    float* noise = (float*)malloc(sizeof(float) * (size_t)B * ad * 3);
+    float* acts_a = (float*)malloc(sizeof(float) * na.S);
+    double* test_tmp = (double*)malloc(sizeof(double) * (c->test_episodes > 0 ? c->test_episodes : 1));
+    int rb_ptr = 0, rb_size = 0, n_ep = 0, timed_out = 0, total_it = 0, test_calls = 0;
+    int64_t train_steps = 0, learn_iters = 0, test_steps = 0;
+    const double T0 = tc->gumbel_temp, Tstep = (T0 / 20.0 - T0) / 1999.0;   /* np.linspace(T0, T0/20, 2000) :59 */
+    float temp = (float)T0;                                                  /* self.gumbel_temp_annealed */
+    const int rule_virtual = (!c->use_test_env && c->env_kind == LE_ENV_SE);
+#define TD3_TEST(dst)                                                                                                              \
+    do {                                                                                                                           \
+        for (int ep_ = 0; ep_ < c->test_episodes; ++ep_) {                                                                         \
+            uint32_t w_[4]; le_oracle_philox((uint32_t)test_calls, (uint32_t)ep_, LE_P_RESET_TEST, 0, k0, k1, w_);                 \
+            double st_[4]; real_reset(c->real_env, w_, st_);                                                                       \
+            float obs_[LE_ORACLE_MAX_SD]; le_oracle_real_obs(c->real_env, st_, obs_);                                              \
+            int el_ = 0; float er_ = 0.f;                                                                                          \
+            for (int t_ = 0; t_ < c->max_steps; t_ += K) {                                                                         \
+                float av_[LE_ORACLE_MAX_AD], r_ = 0.f, d_ = 0.f; double rs_ = 0.0;                                                 \
+                const int a_ = td3_act(tc, &na, actor, acts_a, obs_, temp, k0, k1, 1u, (uint32_t)test_steps, av_);                 \
+                for (int k_ = 0; k_ < K; ++k_) { float rk_; le_oracle_real_step(c->real_env, c->max_steps, st_, &el_, a_, obs_, &rk_, &d_); \
+                                                 rs_ += (double)rk_; if (d_ > 0.5f) break; }                                       \
+                r_ = (float)rs_; er_ += r_; test_steps++;                                                                          \
+                if (d_ > 0.5f) break;                                                                                              \
+            }                                                                                                                      \
+            (dst)[ep_] = (double)er_;                                                                                              \
+        }                                                                                                                          \
+        test_calls++;                                                                                                              \
+    } while (0)
+    for (int episode = 0; episode < c->train_episodes; ++episode) {
+        if (c->step_budget > 0 && train_steps >= c->step_budget) { timed_out = 1; break; }
+        uint32_t w[4];
+        le_oracle_philox((uint32_t)episode, 0, LE_P_RESET_TRAIN, 0, k0, k1, w);
+        double st[4]; real_reset(c->real_env, w, st);
+        float state[LE_ORACLE_MAX_SD]; le_oracle_real_obs(c->real_env, st, state);
+        int elapsed = 0, ep_len = 0; float ep_rew = 0.f;
+        for (int t = 0; t < c->max_steps; t += K) {
+            float avec[LE_ORACLE_MAX_AD]; int a;
+            if (episode < c->init_episodes) {     /* env.get_random_action() -> one-hot (:156-159) */
+                le_oracle_philox((uint32_t)train_steps, 0, LE_P_ACT, 0, k0, k1, w);
+                a = (int)mulhi32(w[1], (uint32_t)ad);
+                for (int k = 0; k < ad; ++k) avec[k] = k == a ? 1.f : 0.f;
+            } else a = td3_act(tc, &na, actor, acts_a, state, temp, k0, k1, 0u, (uint32_t)train_steps, avec);
+            float ns[LE_ORACLE_MAX_SD], r = 0.f, d = 0.f;
+            if (c->env_kind == LE_ENV_SE) {
+                float cur[LE_ORACLE_MAX_SD]; memcpy(cur, state, sizeof(float) * sd);
+                for (int k = 0; k < K; ++k) { float rk; le_oracle_se_step(c, env_theta, cur, a, ns, &rk, &d); r = k == 0 ? rk : r + rk;
+                                              memcpy(cur, ns, sizeof(float) * sd); }
+            } else {
+                float cur[LE_ORACLE_MAX_SD]; memcpy(cur, state, sizeof(float) * sd);
+                double rsum = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    float rr, rk;
+                    le_oracle_real_step(c->real_env, c->max_steps, st, &elapsed, a, ns, &rr, &d);
+                    if (c->env_kind == LE_ENV_RN) { if (le_oracle_rn_reward(c, env_theta, cur, ns, rr, &rk) != 0) return -2; } else rk = rr;
+                    rsum += (double)rk; memcpy(cur, ns, sizeof(float) * sd);
+                    if (d > 0.5f) break;
+                }
+                r = (float)rsum;
+            }
+            float* row = rb + (size_t)rb_ptr * ROW;      /* replay_buffer.add with the action VECTOR (agents/base_agent.py:72-77,119) */
+            memcpy(row, state, sizeof(float) * sd); memcpy(row + sd, avec, sizeof(float) * ad);
+            memcpy(row + sd + ad, ns, sizeof(float) * sd); row[2 * sd + ad] = r; row[2 * sd + ad + 1] = d;
+            rb_ptr = (rb_ptr + 1) % rb_cap; rb_size = rb_size + 1 < rb_cap ? rb_size + 1 : rb_cap;
+            memcpy(state, ns, sizeof(float) * sd);
+            ep_rew += r; ep_len += K;
+            float loss = NAN;
+            if (episode >= c->init_episodes) {
+                temp = (float)(total_it >= 1999 ? T0 / 20.0 : (double)total_it * Tstep + T0);   /* gumbel_temp_anneal_steps[total_it] :64-67 */
+                total_it += 1;
+                for (int b = 0; b < B; b += 4) {
+                    le_oracle_philox((uint32_t)learn_iters, (uint32_t)(b >> 2), LE_P_SAMPLE, 0, k0, k1, w);
+                    for (int k = 0; k < 4 && b + k < B; ++k)
+                        memcpy(batch + (size_t)(b + k) * ROW, rb + (size_t)mulhi32(w[k], (uint32_t)rb_size) * ROW, sizeof(float) * ROW);
+                }
+                le_oracle_td3_normal(k0, k1, 2u, (uint32_t)learn_iters, B * ad, noise);
+                le_oracle_td3_expo(k0, k1, 2u, (uint32_t)learn_iters, B * ad, noise + (size_t)B * ad);
+                le_oracle_td3_expo(k0, k1, 3u, (uint32_t)learn_iters, B * ad, noise + (size_t)2 * B * ad);
+                float aloss;
+                loss = le_oracle_td3_learn(sd, ad, H, L, c->q_act, c->gamma, c->tau, c->lr, tc->policy_delay, (float)tc->max_action,
+                                           (float)tc->policy_std, (float)tc->policy_std_clip, temp, tc->gumbel_hard, actor, actorT, c1, c1T,
+                                           c2, c2T, m_a, v_a, m_c1, v_c1, m_c2, v_c2, &t_actor, &t_critic, total_it, batch, B, noise,
+                                           noise + (size_t)B * ad, noise + (size_t)2 * B * ad, &aloss);
+                learn_iters++;
+            }
+            if (tr && tr->cap > 0 && train_steps < tr->cap) {
+                const int64_t i = train_steps;
+                tr->action[i] = a; tr->explore[i] = episode < c->init_episodes; tr->reward[i] = r; tr->done[i] = d; tr->loss[i] = loss;
+                memcpy(tr->next_state + i * sd, ns, sizeof(float) * sd);
+            }
+            train_steps++;
+            if (d > 0.5f) break;
+        }
+        lengths[n_ep] = ep_len;
+        if (c->use_test_env) {
+            TD3_TEST(test_tmp);
+            double s = 0.0; for (int i = 0; i < c->test_episodes; ++i) s += test_tmp[i];
+            rewards[n_ep] = s / (double)c->test_episodes;
+        } else rewards[n_ep] = (double)ep_rew;
+        n_ep++;
+        if (episode >= c->init_episodes) {
+            const double avg = mean_window(rewards, n_ep, c->early_out_num, 0), avg_last = mean_window(rewards, n_ep, c->early_out_num, c->early_out_num);
+            const int solved = rule_virtual ? ((fabs(avg - avg_last) / (fabs(avg_last) + 1e-9) < c->early_out_virtual_diff) &&
+                                               (episode >= c->init_episodes + c->early_out_num))
+                                            : (avg >= c->solved_reward);
+            if (solved) break;
+        }
+    }
+    double score = 0.0;
+    if (c->final_test) {
+        TD3_TEST(test_rewards);
+        for (int i = 0; i < c->test_episodes; ++i) score += test_rewards[i];
+        score /= (double)c->test_episodes;
+    }
+#undef TD3_TEST
+    out->n_episodes = n_ep; out->timed_out = timed_out; out->train_steps = train_steps; out->learn_iters = learn_iters;
+    out->test_steps = test_steps; out->score = score;
+    if (actor_final) memcpy(actor_final, actor, sizeof(float) * na.P);
+    free(nets); free(mom); free(rb); free(batch); free(noise); free(acts_a); free(test_tmp);
+    return 0;
+}
+
 /* torch default nn.Linear init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias, drawn from the
  * P_QINIT stream in canonical parameter order (distribution of models/model_utils.py:31,38; the stream is ours). */
 void le_oracle_q_init(const le_lane_cfg* c, uint32_t k0, uint32_t k1, float* th) {

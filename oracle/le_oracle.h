@@ -16,6 +16,8 @@
 #define LE_P_RESET_TEST 4
 #define LE_P_QINIT 5
 #define LE_P_NOISE 6
+#define LE_P_TD3_EXPO 8
+#define LE_P_TD3_NORMAL 9
 
 void le_oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]);
 int le_oracle_mlp_params(int in, int H, int out);
@@ -50,5 +52,17 @@ float le_oracle_td3_learn(int sd, int ad, int H, int L, int act, double gamma, d
                           float* m_a, float* v_a, float* m_c1, float* v_c1, float* m_c2, float* v_c2, int32_t* t_actor, int32_t* t_critic,
                           int total_it, const float* rows, int B, const float* policy_noise, const float* expo_target,
                           const float* expo_actor, float* actor_loss);
+
+/* TD3_discrete_vary inner loop (BaseAgent.train/test with the TD3 act/learn): groundwork, oracle only */
+typedef struct le_oracle_td3_cfg {
+    le_lane_cfg base;              /* env / loop / Adam fields; q_hidden, q_layers, q_act = shape of the actor and critic MLPs */
+    int32_t policy_delay, gumbel_hard;
+    double action_std, policy_std, policy_std_clip, gumbel_temp, max_action;
+} le_oracle_td3_cfg;
+void le_oracle_td3_expo(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out);
+void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out);
+int le_oracle_run_lane_td3(const le_oracle_td3_cfg* tc, const float* env_theta, uint32_t k0, uint32_t k1, const float* actor_init,
+                           const float* c1_init, const float* c2_init, float* actor_final, le_lane_out* out, double* rewards,
+                           int32_t* lengths, double* test_rewards, const le_trace* tr);
 
 #endif

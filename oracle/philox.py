@@ -17,6 +17,13 @@ Stream layout — per *lane* (one agent = one (member, variant, eval) of the NES
   P_QINIT       (block, 0)             Q-net init U(-1/sqrt(fan_in), +1/sqrt(fan_in)), params 4*block..
   P_NOISE       (block, member)        NES perturbation normals (key = (seed, generation)), Box-Muller in fp64
 
+  P_TD3_EXPO    (c0, phase) + block    Exp(1) draws of F.gumbel_softmax (TD3_discrete groundwork): e = -ln((w+0.5)*2^-32) in fp64 -> f32;
+                                       phase 0: train action (c0 = train_step), 1: test action (c0 = test step of the lane),
+                                       2: target policy in learn (c0 = learn_iter), 3: policy update in learn; the 4th counter word
+                                       is the block index (draws 4*block .. 4*block+3, row-major over [B][action_dim])
+  P_TD3_NORMAL  (c0, phase) + block    N(0,1) draws (Box-Muller as P_NOISE): phase 0 train action noise, 1 test action noise,
+                                       2 policy noise of learn (randn_like(actions))
+
 uniform in [lo,hi):  lo + (hi-lo) * (w * 2^-32)   evaluated in float64.
 """
 import numpy as np
@@ -34,6 +41,8 @@ P_RESET_TEST = 4
 P_QINIT = 5
 P_NOISE = 6
 P_HP = 7
+P_TD3_EXPO = 8
+P_TD3_NORMAL = 9
 
 
 def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):
@@ -120,3 +129,26 @@ def lane_key(seed, generation, member, variant, eval_idx=0):
     (seed, 0x4C414E45 'LANE') on counter (generation, member, variant, eval_idx)."""
     w = philox4x32(generation, member, variant, eval_idx, seed, 0x4C414E45)
     return (w[0], w[1])
+
+
+def td3_expo(key, phase, c0, n):
+    """n Exp(1) draws (float32) of the P_TD3_EXPO stream."""
+    nblk = (n + 3) // 4
+    w = philox4x32_np(np.uint64(c0), np.uint64(phase), P_TD3_EXPO, np.arange(nblk, dtype=np.uint64), key[0], key[1]).reshape(-1)[:n]
+    u = (w.astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+    return (-np.log(u)).astype(np.float32)
+
+
+def td3_normal(key, phase, c0, n):
+    """n N(0,1) draws (float32) of the P_TD3_NORMAL stream (same Box-Muller as normals())."""
+    nblk = (n + 3) // 4
+    w = philox4x32_np(np.uint64(c0), np.uint64(phase), P_TD3_NORMAL, np.arange(nblk, dtype=np.uint64), key[0], key[1]).astype(np.float64)
+    out = np.empty((nblk, 4), dtype=np.float64)
+    for a, b, o in ((0, 1, 0), (2, 3, 2)):
+        u1 = (w[:, a] + 1.0) * (1.0 / 4294967296.0)
+        u2 = w[:, b] * (1.0 / 4294967296.0)
+        r = np.sqrt(-2.0 * np.log(u1))
+        t = (2.0 * np.pi) * u2
+        out[:, o] = r * np.cos(t)
+        out[:, o + 1] = r * np.sin(t)
+    return out.reshape(-1)[:n].astype(np.float32)

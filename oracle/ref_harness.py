@@ -13,6 +13,9 @@ of the reference's inner loop is redirected to the Philox4x32-10 lane streams of
     env.action_space.sample()            (envs/env_wrapper.py:88)       -> P_ACT word 1
     np.random.randint(0, size, B)        (utils.py:35)                  -> P_SAMPLE
     real-env reset() uniform draw        (gym classic_control)          -> P_RESET_TRAIN / P_RESET_TEST
+    TD3_discrete_vary only (Td3RngInjector):
+    Tensor.exponential_() in F.gumbel_softmax (models/actor_critic.py:36) -> P_TD3_EXPO
+    torch.randn / torch.randn_like       (agents/TD3_discrete_vary.py:75,162,166) -> P_TD3_NORMAL
 """
 import contextlib
 import os
@@ -177,3 +180,79 @@ def injected_rng(inj, reset_envs=(), action_spaces=()):
             e.reset_hook = None
         for sp in action_spaces:
             sp.sample_hook = None
+
+
+class Td3RngInjector(LaneRngInjector):
+    """LaneRngInjector plus the torch draws of TD3_discrete_vary (agents/TD3_discrete_vary.py:73-75,155-166 and the
+    exponential_() inside F.gumbel_softmax) on the P_TD3_EXPO / P_TD3_NORMAL streams of oracle/philox.py."""
+
+    def __init__(self, key, action_dim, real_env_kind):
+        super().__init__(key, action_dim, real_env_kind)
+        self.test_steps = 0
+        self.ctx = None          # ("train" | "test" | "learn", c0); learn: expo call count selects phase 2 / 3
+        self.learn_expo_calls = 0
+
+    def action_sample(self, space):      # env.get_random_action() of the init episodes: P_ACT word 1 of this train step
+        w = self.px.philox4x32(self.train_steps, 0, self.px.P_ACT, 0, *self.key)
+        return int((int(w[1]) * self.ad) >> 32)
+
+    def expo(self, n):
+        kind, c0 = self.ctx
+        if kind == "learn":
+            phase = 2 + self.learn_expo_calls
+            self.learn_expo_calls += 1
+        else:
+            phase = 0 if kind == "train" else 1
+        return self.px.td3_expo(self.key, phase, c0, n)
+
+    def normal(self, n):
+        kind, c0 = self.ctx
+        return self.px.td3_normal(self.key, {"train": 0, "test": 1, "learn": 2}[kind], c0, n)
+
+
+@contextlib.contextmanager
+def injected_rng_td3(inj, agent, reset_envs=(), action_spaces=()):
+    """injected_rng for a TD3_discrete_vary agent: additionally patches torch.randn / torch.randn_like /
+    Tensor.exponential_ and wraps the agent's select_*_action / learn so that every draw knows its stream position."""
+    import torch
+    orig = (torch.randn, torch.randn_like, torch.Tensor.exponential_, agent.select_train_action, agent.select_test_action, agent.learn)
+
+    def fake_randn(*size, **kw):
+        shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        return torch.from_numpy(inj.normal(int(torch.Size(shape).numel())).reshape(shape))
+
+    def fake_randn_like(t, **kw):
+        return torch.from_numpy(inj.normal(t.numel()).reshape(tuple(t.shape)))
+
+    def fake_exponential_(self, lambd=1.0, generator=None):
+        with torch.no_grad():
+            self.copy_(torch.from_numpy(inj.expo(self.numel()).reshape(tuple(self.shape))))
+        return self
+
+    def select_train(state, env, episode):
+        inj.ctx = ("train", inj.train_steps)
+        try:
+            return orig[3](state=state, env=env, episode=episode)
+        finally:
+            inj.train_steps += 1
+
+    def select_test(state, env):
+        inj.ctx = ("test", inj.test_steps)
+        try:
+            return orig[4](state, env)
+        finally:
+            inj.test_steps += 1
+
+    def learn(replay_buffer, env, episode):
+        inj.ctx = ("learn", inj.learn_iters)      # replay_buffer.sample() inside increments learn_iters afterwards
+        inj.learn_expo_calls = 0
+        return orig[5](replay_buffer=replay_buffer, env=env, episode=episode)
+
+    torch.randn, torch.randn_like, torch.Tensor.exponential_ = fake_randn, fake_randn_like, fake_exponential_
+    agent.select_train_action, agent.select_test_action, agent.learn = select_train, select_test, learn
+    try:
+        with injected_rng(inj, reset_envs=reset_envs, action_spaces=action_spaces):
+            yield inj
+    finally:
+        torch.randn, torch.randn_like, torch.Tensor.exponential_ = orig[:3]
+        agent.select_train_action, agent.select_test_action, agent.learn = orig[3:]

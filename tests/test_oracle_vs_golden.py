@@ -131,3 +131,26 @@ def test_td3_discrete_learn_restatement_vs_reference_golden():
             err = np.abs(nets[n] - g["after_" + n][k]).max()      # weights move by ~lr = 1.7e-3 per step; observed error ~1 ulp
             assert err < 1e-6, (k, n, err)
     assert counters == [int(g["updated"].sum()), len(g["temps"])]
+
+
+def test_td3_discrete_trajectory_lockstep_vs_reference_golden():
+    """Groundwork for SURVEY §8(f) rank 2: the whole TD3_discrete_vary lane (BaseAgent.train with per-episode test() + final
+    test(), Gumbel-softmax acting, learn()) restated in C, in lock-step with the unmodified reference under RNG injection."""
+    import json
+    g = load_golden("trajectory_td3_cartpole_se.npz")
+    base = cfg_from_bytes(g["cfg"])
+    tcfg = c_oracle.td3_cfg(base, json.loads(str(g["agent_cfg_json"])), float(g["max_action"]))
+    key = tuple(int(k) for k in g["key"])
+    cap = len(g["action"])
+    res = c_oracle.run_lane_td3(tcfg, g["env_theta"], key, g["init_actor"], g["init_critic_1"], g["init_critic_2"], trace_cap=cap)
+    tr = res["trace"]
+    n = sync_prefix(g["action"], tr.action)
+    assert n >= min(cap, 300), "restatement left the reference trajectory after %d steps" % n
+    assert rel_err(tr.next_state[:n], g["next_state"][:n], 1e-3) < 2e-4
+    assert rel_err(tr.reward[:n], g["reward"][:n], 1e-3) < 2e-4
+    assert np.array_equal(tr.done[:n] > 0.5, g["done"][:n] > 0.5)
+    if n == int(g["train_steps"]) == res["train_steps"]:
+        assert np.array_equal(res["lengths"], g["lengths"])
+        assert np.allclose(res["rewards"], g["rewards"]) and np.allclose(res["test_rewards"], g["test_rewards"])
+        assert res["learn_iters"] == int(g["learn_iters"])
+        assert np.abs(res["actor_final"] - g["actor_final"]).max() < 1e-4      # after 600 learn() calls / 300 policy updates (observed 7e-6)
