@@ -810,17 +810,17 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
 /* ------------------------------------------------------------------------------------------------ */
 /* TD3_discrete_vary lane: BaseAgent.train / test (agents/base_agent.py:64-227) with select_train_action / select_test_action
  * (agents/TD3_discrete_vary.py:155-166) and learn (:62-119).  Streams: oracle/philox.py P_TD3_EXPO / P_TD3_NORMAL. */
-void le_oracle_td3_expo(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out) {
+void le_oracle_td3_expo(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, uint32_t sub, int n, float* out) {
     for (int i = 0; i < n; i += 4) {
         uint32_t w[4];
-        le_oracle_philox(c0, phase, LE_P_TD3_EXPO, (uint32_t)(i >> 2), k0, k1, w);
+        le_oracle_philox(c0, phase, LE_P_TD3_EXPO, (uint32_t)(i >> 2) + (sub << 16), k0, k1, w);
         for (int k = 0; k < 4 && i + k < n; ++k) out[i + k] = (float)(-log(((double)w[k] + 0.5) * (1.0 / 4294967296.0)));
     }
 }
-void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out) {
+void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, uint32_t sub, int n, float* out) {
     for (int i = 0; i < n; i += 4) {
         uint32_t w[4];
-        le_oracle_philox(c0, phase, LE_P_TD3_NORMAL, (uint32_t)(i >> 2), k0, k1, w);
+        le_oracle_philox(c0, phase, LE_P_TD3_NORMAL, (uint32_t)(i >> 2) + (sub << 16), k0, k1, w);
         double z[4];
         for (int h = 0; h < 2; ++h) {
             const double u1 = ((double)w[2 * h] + 1.0) * (1.0 / 4294967296.0), u2 = (double)w[2 * h + 1] * (1.0 / 4294967296.0);
@@ -833,13 +833,13 @@ void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0,
 
 /* actor(state, temp) + randn(ad) * action_std -> action vector; returns its argmax (first maximum) */
 static int td3_act(const le_oracle_td3_cfg* tc, const omlp* na, const float* actor, float* acts, const float* state, float temp,
-                   uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, float* avec) {
+                   uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, uint32_t sub, float* avec) {
     const int ad = tc->base.ad;
     float logits[LE_ORACLE_MAX_AD] = {0}, expo[LE_ORACLE_MAX_AD], nz[LE_ORACLE_MAX_AD], ysoft[LE_ORACLE_MAX_AD], ret[LE_ORACLE_MAX_AD];
     const float* o = mlp_fwd_row(na, actor, state, acts);
     for (int k = 0; k < ad; ++k) logits[k] = o[k] * (float)tc->max_action;
-    le_oracle_td3_expo(k0, k1, phase, c0, ad, expo);
-    le_oracle_td3_normal(k0, k1, phase, c0, ad, nz);
+    le_oracle_td3_expo(k0, k1, phase, c0, sub, ad, expo);
+    le_oracle_td3_normal(k0, k1, phase, c0, sub, ad, nz);
     gumbel_softmax_row(logits, expo, ad, temp, tc->gumbel_hard, ysoft, ret);
     int best = 0;
     for (int k = 0; k < ad; ++k) { avec[k] = ret[k] + nz[k] * (float)tc->action_std; if (avec[k] > avec[best]) best = k; }
@@ -884,7 +884,7 @@ int le_oracle_run_lane_td3(const le_oracle_td3_cfg* tc, const float* env_theta, 
             int el_ = 0; float er_ = 0.f;                                                                                          \
             for (int t_ = 0; t_ < c->max_steps; t_ += K) {                                                                         \
                 float av_[LE_ORACLE_MAX_AD], r_ = 0.f, d_ = 0.f; double rs_ = 0.0;                                                 \
-                const int a_ = td3_act(tc, &na, actor, acts_a, obs_, temp, k0, k1, 1u, (uint32_t)test_steps, av_);                 \
+                const int a_ = td3_act(tc, &na, actor, acts_a, obs_, temp, k0, k1, 1u, ((uint32_t)test_calls << 16) | (uint32_t)(t_ / K), (uint32_t)ep_, av_);                 \
                 for (int k_ = 0; k_ < K; ++k_) { float rk_; le_oracle_real_step(c->real_env, c->max_steps, st_, &el_, a_, obs_, &rk_, &d_); \
                                                  rs_ += (double)rk_; if (d_ > 0.5f) break; }                                       \
                 r_ = (float)rs_; er_ += r_; test_steps++;                                                                          \
@@ -907,7 +907,7 @@ int le_oracle_run_lane_td3(const le_oracle_td3_cfg* tc, const float* env_theta, 
                 le_oracle_philox((uint32_t)train_steps, 0, LE_P_ACT, 0, k0, k1, w);
                 a = (int)mulhi32(w[1], (uint32_t)ad);
                 for (int k = 0; k < ad; ++k) avec[k] = k == a ? 1.f : 0.f;
-            } else a = td3_act(tc, &na, actor, acts_a, state, temp, k0, k1, 0u, (uint32_t)train_steps, avec);
+            } else a = td3_act(tc, &na, actor, acts_a, state, temp, k0, k1, 0u, (uint32_t)train_steps, 0u, avec);
             float ns[LE_ORACLE_MAX_SD], r = 0.f, d = 0.f;
             if (c->env_kind == LE_ENV_SE) {
                 float cur[LE_ORACLE_MAX_SD]; memcpy(cur, state, sizeof(float) * sd);
@@ -940,9 +940,9 @@ int le_oracle_run_lane_td3(const le_oracle_td3_cfg* tc, const float* env_theta, 
                     for (int k = 0; k < 4 && b + k < B; ++k)
                         memcpy(batch + (size_t)(b + k) * ROW, rb + (size_t)mulhi32(w[k], (uint32_t)rb_size) * ROW, sizeof(float) * ROW);
                 }
-                le_oracle_td3_normal(k0, k1, 2u, (uint32_t)learn_iters, B * ad, noise);
-                le_oracle_td3_expo(k0, k1, 2u, (uint32_t)learn_iters, B * ad, noise + (size_t)B * ad);
-                le_oracle_td3_expo(k0, k1, 3u, (uint32_t)learn_iters, B * ad, noise + (size_t)2 * B * ad);
+                le_oracle_td3_normal(k0, k1, 2u, (uint32_t)learn_iters, 0u, B * ad, noise);
+                le_oracle_td3_expo(k0, k1, 2u, (uint32_t)learn_iters, 0u, B * ad, noise + (size_t)B * ad);
+                le_oracle_td3_expo(k0, k1, 3u, (uint32_t)learn_iters, 0u, B * ad, noise + (size_t)2 * B * ad);
                 float aloss;
                 loss = le_oracle_td3_learn(sd, ad, H, L, c->q_act, c->gamma, c->tau, c->lr, tc->policy_delay, (float)tc->max_action,
                                            (float)tc->policy_std, (float)tc->policy_std_clip, temp, tc->gumbel_hard, actor, actorT, c1, c1T,

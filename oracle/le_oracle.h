@@ -59,8 +59,8 @@ typedef struct le_oracle_td3_cfg {
     int32_t policy_delay, gumbel_hard;
     double action_std, policy_std, policy_std_clip, gumbel_temp, max_action;
 } le_oracle_td3_cfg;
-void le_oracle_td3_expo(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out);
-void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, int n, float* out);
+void le_oracle_td3_expo(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, uint32_t sub, int n, float* out);
+void le_oracle_td3_normal(uint32_t k0, uint32_t k1, uint32_t phase, uint32_t c0, uint32_t sub, int n, float* out);
 int le_oracle_run_lane_td3(const le_oracle_td3_cfg* tc, const float* env_theta, uint32_t k0, uint32_t k1, const float* actor_init,
                            const float* c1_init, const float* c2_init, float* actor_final, le_lane_out* out, double* rewards,
                            int32_t* lengths, double* test_rewards, const le_trace* tr);

@@ -18,7 +18,8 @@ Stream layout — per *lane* (one agent = one (member, variant, eval) of the NES
   P_NOISE       (block, member)        NES perturbation normals (key = (seed, generation)), Box-Muller in fp64
 
   P_TD3_EXPO    (c0, phase) + block    Exp(1) draws of F.gumbel_softmax (TD3_discrete groundwork): e = -ln((w+0.5)*2^-32) in fp64 -> f32;
-                                       phase 0: train action (c0 = train_step), 1: test action (c0 = test step of the lane),
+                                       phase 0: train action (c0 = train_step), 1: test action (c0 = test_call << 16 | step in the episode, episode in
+                                       bits 16.. of the 4th counter word: test episodes are independent, so they can run in parallel),
                                        2: target policy in learn (c0 = learn_iter), 3: policy update in learn; the 4th counter word
                                        is the block index (draws 4*block .. 4*block+3, row-major over [B][action_dim])
   P_TD3_NORMAL  (c0, phase) + block    N(0,1) draws (Box-Muller as P_NOISE): phase 0 train action noise, 1 test action noise,
@@ -131,18 +132,18 @@ def lane_key(seed, generation, member, variant, eval_idx=0):
     return (w[0], w[1])
 
 
-def td3_expo(key, phase, c0, n):
-    """n Exp(1) draws (float32) of the P_TD3_EXPO stream."""
+def td3_expo(key, phase, c0, n, sub=0):
+    """n Exp(1) draws (float32) of the P_TD3_EXPO stream (sub: bits 16.. of the 4th counter word, the test episode)."""
     nblk = (n + 3) // 4
-    w = philox4x32_np(np.uint64(c0), np.uint64(phase), P_TD3_EXPO, np.arange(nblk, dtype=np.uint64), key[0], key[1]).reshape(-1)[:n]
+    w = philox4x32_np(np.uint64(c0), np.uint64(phase), P_TD3_EXPO, np.arange(nblk, dtype=np.uint64) + np.uint64(sub << 16), key[0], key[1]).reshape(-1)[:n]
     u = (w.astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
     return (-np.log(u)).astype(np.float32)
 
 
-def td3_normal(key, phase, c0, n):
+def td3_normal(key, phase, c0, n, sub=0):
     """n N(0,1) draws (float32) of the P_TD3_NORMAL stream (same Box-Muller as normals())."""
     nblk = (n + 3) // 4
-    w = philox4x32_np(np.uint64(c0), np.uint64(phase), P_TD3_NORMAL, np.arange(nblk, dtype=np.uint64), key[0], key[1]).astype(np.float64)
+    w = philox4x32_np(np.uint64(c0), np.uint64(phase), P_TD3_NORMAL, np.arange(nblk, dtype=np.uint64) + np.uint64(sub << 16), key[0], key[1]).astype(np.float64)
     out = np.empty((nblk, 4), dtype=np.float64)
     for a, b, o in ((0, 1, 0), (2, 3, 2)):
         u1 = (w[:, a] + 1.0) * (1.0 / 4294967296.0)

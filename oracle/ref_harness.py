@@ -188,26 +188,31 @@ class Td3RngInjector(LaneRngInjector):
 
     def __init__(self, key, action_dim, real_env_kind):
         super().__init__(key, action_dim, real_env_kind)
-        self.test_steps = 0
-        self.ctx = None          # ("train" | "test" | "learn", c0); learn: expo call count selects phase 2 / 3
+        self.test_step_in_ep = 0
+        self.ctx = None          # ("train" | "test" | "learn", c0, sub); learn: expo call count selects phase 2 / 3
         self.learn_expo_calls = 0
 
     def action_sample(self, space):      # env.get_random_action() of the init episodes: P_ACT word 1 of this train step
         w = self.px.philox4x32(self.train_steps, 0, self.px.P_ACT, 0, *self.key)
         return int((int(w[1]) * self.ad) >> 32)
 
+    def reset_draw(self, env):
+        if self.in_test:
+            self.test_step_in_ep = 0
+        return super().reset_draw(env)
+
     def expo(self, n):
-        kind, c0 = self.ctx
+        kind, c0, sub = self.ctx
         if kind == "learn":
             phase = 2 + self.learn_expo_calls
             self.learn_expo_calls += 1
         else:
             phase = 0 if kind == "train" else 1
-        return self.px.td3_expo(self.key, phase, c0, n)
+        return self.px.td3_expo(self.key, phase, c0, n, sub)
 
     def normal(self, n):
-        kind, c0 = self.ctx
-        return self.px.td3_normal(self.key, {"train": 0, "test": 1, "learn": 2}[kind], c0, n)
+        kind, c0, sub = self.ctx
+        return self.px.td3_normal(self.key, {"train": 0, "test": 1, "learn": 2}[kind], c0, n, sub)
 
 
 @contextlib.contextmanager
@@ -230,21 +235,21 @@ def injected_rng_td3(inj, agent, reset_envs=(), action_spaces=()):
         return self
 
     def select_train(state, env, episode):
-        inj.ctx = ("train", inj.train_steps)
+        inj.ctx = ("train", inj.train_steps, 0)
         try:
             return orig[3](state=state, env=env, episode=episode)
         finally:
             inj.train_steps += 1
 
     def select_test(state, env):
-        inj.ctx = ("test", inj.test_steps)
+        inj.ctx = ("test", (inj.test_calls << 16) | inj.test_step_in_ep, inj.test_episode - 1)
         try:
             return orig[4](state, env)
         finally:
-            inj.test_steps += 1
+            inj.test_step_in_ep += 1
 
     def learn(replay_buffer, env, episode):
-        inj.ctx = ("learn", inj.learn_iters)      # replay_buffer.sample() inside increments learn_iters afterwards
+        inj.ctx = ("learn", inj.learn_iters, 0)   # replay_buffer.sample() inside increments learn_iters afterwards
         inj.learn_expo_calls = 0
         return orig[5](replay_buffer=replay_buffer, env=env, episode=episode)
 
