@@ -215,6 +215,30 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
                            double* test_rewards, int device);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* TD3_discrete_vary lanes (agents/TD3_discrete_vary.py, models/actor_critic.py:22-36,69-76)  */
+
+/* base: env / loop / Adam fields as for DDQN lanes (eps_* unused); q_hidden, q_layers, q_act give the shape of the actor
+ * (sd -> H x L -> ad) and of the two critics (sd+ad -> H x L -> 1). */
+typedef struct le_td3_cfg {
+    le_lane_cfg base;
+    int32_t policy_delay;    /* agents/TD3_discrete_vary.py:35 */
+    int32_t gumbel_hard;     /* gumbel_softmax_hard (models/actor_critic.py:32) */
+    double action_std, policy_std, policy_std_clip; /* :37-39 */
+    double gumbel_temp;      /* gumbel_softmax_temp, annealed to /20 over 2000 learn() calls (:58-59) */
+    double max_action;       /* envs/env_wrapper.py:106-110 */
+} le_td3_cfg;
+
+/* n_lanes complete train(+per-episode test)+test runs of TD3_discrete_vary agents (the DDQN lanes' le_inner_loop_run_host
+ * for this agent family), HOST buffers in and out.  actor_init [n_init][P_actor], critic1_init / critic2_init
+ * [n_init][P_critic] with n_init = 1 (shared by all lanes) or n_lanes; parameter vectors in torch state_dict order.
+ * Training env: LE_ENV_SE or LE_ENV_REAL.  trace_host (may be NULL): HOST arrays recording lane `trace_lane`.           */
+int le_td3_param_counts(const le_td3_cfg* cfg, int* p_actor, int* p_critic);
+int le_td3_run_host(const le_td3_cfg* cfg, const float* env_theta, int n_env, const int32_t* env_index, const uint32_t* keys,
+                    const float* actor_init, const float* critic1_init, const float* critic2_init, int n_init, float* actor_final,
+                    int n_lanes, le_lane_out* out, double* rewards, int32_t* lengths, double* test_rewards,
+                    const le_trace* trace_host, int trace_lane, int device);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* NES outer step (agents/GTN_worker.py:156-185, agents/GTN_master.py:267-298)                        */
 
 /* get_random_noise + add_noise (+/-): out[(m*3+v)][P] = theta + sign_v * noise_std * N(0,1), v in

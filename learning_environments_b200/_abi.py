@@ -77,6 +77,12 @@ class LaneCfg(C.Structure):
         return self.q_kind == Q_DQN and self.q_layers <= 1 and self.q_hidden <= 128
 
 
+class Td3Cfg(C.Structure):
+    """struct le_td3_cfg (include/le_b200.h): TD3_discrete_vary lanes."""
+    _fields_ = [("base", LaneCfg), ("policy_delay", C.c_int32), ("gumbel_hard", C.c_int32), ("action_std", C.c_double),
+                ("policy_std", C.c_double), ("policy_std_clip", C.c_double), ("gumbel_temp", C.c_double), ("max_action", C.c_double)]
+
+
 class LaneOut(C.Structure):
     """struct le_lane_out."""
     _fields_ = [
@@ -120,6 +126,7 @@ EXPORTED_SYMBOLS = [
     "le_se_forward", "le_rn_reward", "le_qnet_forward", "le_real_env_step", "le_td_update",
     "le_inner_loop_workspace_bytes", "le_inner_loop_plan", "le_inner_loop_run", "le_inner_loop_run_host",
     "le_nes_perturb", "le_nes_noise", "le_nes_update", "le_nes_partial_update",
+    "le_td3_param_counts", "le_td3_run_host",
 ]
 
 

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "le_general_api.h"
+#include "le_td3_api.h"
 #include "le_instance.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -543,6 +544,124 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == LE_OK) { le_set_error("le_inner_loop_run_host: %s", cudaGetErrorString(e)); rc = LE_ECUDA; }
+    cudaFreeAsync(arena, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+// ---- TD3_discrete_vary lanes ----------------------------------------------------------------------------
+int le_td3_param_counts(const le_td3_cfg* cfg, int* p_actor, int* p_critic) {
+    if (!cfg || cfg->base.q_hidden < 1) { le_set_error("le_td3_param_counts: bad arguments"); return LE_EINVAL; }
+    const int sd = cfg->base.sd, ad = cfg->base.ad, H = cfg->base.q_hidden, L = cfg->base.q_layers > 1 ? cfg->base.q_layers : 1;
+    if (p_actor) *p_actor = sd * H + H + (L - 1) * (H * H + H) + H * ad + ad;
+    if (p_critic) *p_critic = (sd + ad) * H + H + (L - 1) * (H * H + H) + H + 1;
+    return LE_OK;
+}
+
+int le_td3_run_host(const le_td3_cfg* cfg, const float* env_theta, int n_env, const int32_t* env_index, const uint32_t* keys,
+                    const float* actor_init, const float* critic1_init, const float* critic2_init, int n_init, float* actor_final,
+                    int n_lanes, le_lane_out* out, double* rewards, int32_t* lengths, double* test_rewards, const le_trace* trace_host,
+                    int trace_lane, int device) {
+    if (!cfg || !keys || !actor_init || !critic1_init || !critic2_init || !out || !rewards || !lengths || !test_rewards || n_lanes < 1 ||
+        (n_init != 1 && n_init != n_lanes)) {
+        le_set_error("le_td3_run_host: bad arguments");
+        return LE_EINVAL;
+    }
+    const le_lane_cfg* c = &cfg->base;
+    int rc = check_env_cfg(c);
+    if (rc != LE_OK) return rc;
+    if (c->env_kind == LE_ENV_RN) { le_set_error("le_td3_run_host: reward-network training envs are not built for TD3 lanes"); return LE_EUNSUPPORTED; }
+    if (qact_of(c) < 0 || c->q_hidden < 1 || c->q_layers > 3 || cfg->policy_delay < 1 || !(cfg->gumbel_temp > 0.0) || c->ad > 4 ||
+        c->batch_size < 1 || c->train_episodes < 0 || c->test_episodes < 1 || c->max_steps < 1) {
+        le_set_error("le_td3_run_host: configuration outside the compiled kernel set");
+        return LE_EUNSUPPORTED;
+    }
+    const InstanceOps* ops = le_find_instance(c->sd, c->ad, 1, QACT_TANH);
+    if (!ops) { le_set_error("no compiled kernel set for state_dim=%d action_dim=%d", c->sd, c->ad); return LE_EUNSUPPORTED; }
+    LE_CUDA_CHECK(cudaSetDevice(device));
+    int sms = 0;
+    LE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int64_t max_total = (int64_t)c->train_episodes * c->max_steps;
+    if (c->step_budget > 0 && c->step_budget + c->max_steps < max_total) max_total = c->step_budget + c->max_steps;
+    if (max_total < 1) max_total = 1;
+    const int ring_cap = (int)((int64_t)c->rb_size < max_total ? c->rb_size : max_total);
+    Td3Plan tp;
+    rc = td3_plan(cfg, n_lanes, ring_cap, sms, &tp);
+    if (rc != LE_OK) return rc;
+    const int P_env = c->env_kind == LE_ENV_SE ? 3 * c->env_hidden * (c->sd + c->ad + 1) + c->env_hidden * (c->sd + 2) + c->sd + 2 : 0;
+    if (c->env_kind == LE_ENV_SE && (!env_theta || n_env < 1)) { le_set_error("le_td3_run_host: env_theta is required for SE lanes"); return LE_EINVAL; }
+    const int64_t pack_stride_f = (c->env_kind == LE_ENV_SE ? ops->se_pack_vec4(c->env_hidden) : 1) * 4;
+    const int rs = c->train_episodes > 0 ? c->train_episodes : 1;
+    const int tcap = trace_host ? trace_host->cap : 0;
+    cudaStream_t st;
+    LE_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct Seg { const void* src; void* dst_host; size_t bytes; size_t off; };
+    std::vector<Seg> segs;
+    size_t total = 0;
+    auto add = [&](const void* src, void* dst, size_t bytes) { Seg s{src, dst, bytes, total}; total += (bytes + 255) / 256 * 256; segs.push_back(s); return segs.size() - 1; };
+    const size_t i_th = add(env_theta, nullptr, P_env > 0 ? sizeof(float) * (size_t)P_env * n_env : 0);
+    const size_t i_ei = add(env_index, nullptr, env_index ? sizeof(int32_t) * n_lanes : 0);
+    const size_t i_key = add(keys, nullptr, sizeof(uint32_t) * 2 * n_lanes);
+    const size_t i_a = add(actor_init, nullptr, sizeof(float) * (size_t)tp.p_actor * n_init);
+    const size_t i_c1 = add(critic1_init, nullptr, sizeof(float) * (size_t)tp.p_critic * n_init);
+    const size_t i_c2 = add(critic2_init, nullptr, sizeof(float) * (size_t)tp.p_critic * n_init);
+    const size_t i_af = add(nullptr, actor_final, actor_final ? sizeof(float) * (size_t)tp.p_actor * n_lanes : 0);
+    const size_t i_out = add(nullptr, out, sizeof(le_lane_out) * n_lanes);
+    const size_t i_rw = add(nullptr, rewards, sizeof(double) * (size_t)rs * n_lanes);
+    const size_t i_ln = add(nullptr, lengths, sizeof(int32_t) * (size_t)rs * n_lanes);
+    const size_t i_tr = add(nullptr, test_rewards, sizeof(double) * (size_t)c->test_episodes * n_lanes);
+    const size_t i_ta = add(nullptr, tcap ? trace_host->action : nullptr, sizeof(int32_t) * (size_t)tcap);
+    const size_t i_te = add(nullptr, tcap ? trace_host->explore : nullptr, sizeof(int32_t) * (size_t)tcap);
+    const size_t i_tn = add(nullptr, tcap ? trace_host->next_state : nullptr, sizeof(float) * (size_t)tcap * c->sd);
+    const size_t i_trw = add(nullptr, tcap ? trace_host->reward : nullptr, sizeof(float) * (size_t)tcap);
+    const size_t i_td = add(nullptr, tcap ? trace_host->done : nullptr, sizeof(float) * (size_t)tcap);
+    const size_t i_tl = add(nullptr, tcap ? trace_host->loss : nullptr, sizeof(float) * (size_t)tcap);
+    const size_t off_pack = total;
+    total += ((size_t)(n_env > 0 ? n_env : 1) * pack_stride_f * 4 + 255) / 256 * 256;
+    const size_t off_counter = total;
+    total += 256;
+    const size_t off_slots = total;
+    total += (size_t)tp.grid * tp.slot_floats * sizeof(float);
+    char* arena = nullptr;
+    LE_CUDA_CHECK(cudaMallocAsync((void**)&arena, total, st));
+    for (auto& s : segs)
+        if (s.src && s.bytes) LE_CUDA_CHECK(cudaMemcpyAsync(arena + s.off, s.src, s.bytes, cudaMemcpyHostToDevice, st));
+    LE_CUDA_CHECK(cudaMemsetAsync(arena + segs[i_rw].off, 0, segs[i_rw].bytes + segs[i_ln].bytes, st));
+    if (tcap) LE_CUDA_CHECK(cudaMemsetAsync(arena + segs[i_ta].off, 0xff, off_pack - segs[i_ta].off, st));   /* untouched trace slots: -1 / NaN */
+    LE_CUDA_CHECK(cudaMemsetAsync(arena + off_counter, 0, 256, st));
+    auto dp = [&](size_t i) -> char* { return segs[i].bytes ? arena + segs[i].off : nullptr; };
+    if (c->env_kind == LE_ENV_SE) {
+        float slopes[3];
+        for (int i = 0; i < 3; ++i) slopes[i] = act_slope(c->env_act, c->env_slope[i]);
+        LE_CUDA_CHECK(ops->launch_pack_se((const float*)dp(i_th), P_env, n_env, c->env_hidden, slopes, (float*)(arena + off_pack), pack_stride_f, st));
+    }
+    RunParams P;
+    memset(&P, 0, sizeof(P));
+    P.env_pack = (const float4*)(arena + off_pack); P.env_pack_stride = pack_stride_f / 4;
+    P.env_index = (const int32_t*)dp(i_ei); P.keys = (const uint32_t*)dp(i_key);
+    P.n_lanes = n_lanes; P.out = (le_lane_out*)dp(i_out); P.rewards = (double*)dp(i_rw); P.lengths = (int32_t*)dp(i_ln);
+    P.test_rewards = (double*)dp(i_tr);
+    P.rew_stride = rs; P.test_stride = c->test_episodes;
+    P.ring_cap = ring_cap;
+    P.work_counter = (int*)(arena + off_counter);
+    if (tcap) {
+        P.trace.cap = tcap; P.trace.action = (int32_t*)dp(i_ta); P.trace.explore = (int32_t*)dp(i_te); P.trace.next_state = (float*)dp(i_tn);
+        P.trace.reward = (float*)dp(i_trw); P.trace.done = (float*)dp(i_td); P.trace.loss = (float*)dp(i_tl);
+        P.trace_lane = trace_lane;
+    }
+    cudaError_t le = td3_launch(cfg, P, (float*)(arena + off_slots), tp, (const float*)dp(i_a), (const float*)dp(i_c1), (const float*)dp(i_c2),
+                                n_init == n_lanes && n_lanes > 1, (float*)dp(i_af), st);
+    if (le != cudaSuccess) { le_set_error("td3 launch failed: %s", cudaGetErrorString(le)); rc = LE_ECUDA; }
+    if (rc == LE_OK) {
+        for (auto& s : segs)
+            if (s.dst_host && s.bytes) {
+                cudaError_t e = cudaMemcpyAsync(s.dst_host, arena + s.off, s.bytes, cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) { le_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = LE_ECUDA; break; }
+            }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && rc == LE_OK) { le_set_error("le_td3_run_host: %s", cudaGetErrorString(e)); rc = LE_ECUDA; }
     cudaFreeAsync(arena, st);
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);

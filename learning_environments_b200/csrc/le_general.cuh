@@ -77,7 +77,7 @@ __device__ __forceinline__ float g_act_grad(int act, float slope, float h) {
 // covered by 512 FFMA per thread).  Per-thread element coordinates inside a tile-chunk are loop invariants (element q
 // of a thread is its first element plus q constant steps), so a chunk costs one base address per operand.  Warps whose
 // 16 rows lie outside I skip the arithmetic.  The k-summation order per output element is ascending for every shape.
-__device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a_sl, const float* __restrict__ B, int b_sl, int b_sj,
+static __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si, int a_sl, const float* __restrict__ B, int b_sl, int b_sj,
                                     float* __restrict__ C, int c_si, int c_sj, int I, int J, int L, const float* __restrict__ bias,
                                     int act, float slope, bool accumulate, float* sm) {
     constexpr int TM = kGTileM, TN = kGTileN, TK = kGChunk, LDA = TM + kGPad, LDB = TN + kGPad;
@@ -260,7 +260,7 @@ __device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict
 // Dense layer forward with at most 4 output columns and many rows (dueling heads fd -> 1 / fd -> ad): thread b owns
 // batch row b and streams X[b][:] (16-byte loads when aligned); the weights sit in shared memory as Ws[k][4] and are
 // read as broadcasts.  Same ascending-k fmaf chain per output as g_gemm.
-__device__ __noinline__ void g_thinj_fwd(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int B,
+static __device__ __noinline__ void g_thinj_fwd(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int B,
                                          float* __restrict__ acts, int S, float slope, float* sm) {
     constexpr int KB = 1024;
     static_assert(KB * 4 <= kGSmemFloats, "weight stage must fit the GEMM buffer");
@@ -314,7 +314,7 @@ __device__ __forceinline__ void g_layer_fwd(const GLayer& l, const float* th, co
 }
 
 // all layers for B rows; returns nothing: activations are in `acts` (row stride S = net.sum_out)
-__device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm) {
+static __device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm) {
     const int S = n.sum_out;
     const float* in = X;
     int in_s = xs;
@@ -344,7 +344,7 @@ __device__ __forceinline__ float g_block_sum(float v, float* red) {
 }
 
 // q[b][a] for B rows from the activation record: DQN -> output layer; dueling -> V + (A - mean(A over batch x actions))
-__device__ void g_q_values(const GNet& n, const float* acts, int B, float* q, float* red) {
+static __device__ void g_q_values(const GNet& n, const float* acts, int B, float* q, float* red) {
     const int S = n.sum_out, AD = n.ad;
     if (n.kind == LE_Q_DQN) {
         const int yo = n.feat[n.nfeat - 1].y_off;
@@ -365,7 +365,7 @@ __device__ void g_q_values(const GNet& n, const float* acts, int B, float* q, fl
 
 // backward of one dense layer for B rows. dact holds dL/dY at l.y_off (overwritten by dZ); X/xs: the layer's input.
 // dX (may be null) receives / accumulates dL/dX with row stride dxs.
-__device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const float* X, int xs, const float* acts, float* dact,
+static __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const float* X, int xs, const float* acts, float* dact,
                             int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm) {
     // dZ = dY * act'(Y) in place, and db[o] = sum_b dZ[b][o]: thread (rg, o) walks rows rg, rg+RG, ... of column o
     // (coalesced across o, independent loads down the column), partial sums meet in shared memory in fixed order.
@@ -418,7 +418,7 @@ struct GSlot {
 };
 
 // DDQN.learn / DuelingDDQN.learn on the B rows staged in slot.xs / xs2 / misc (misc = [a, r, d, pad] per row)
-__device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red) {
+static __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red) {
     const int S = n.sum_out, AD = n.ad, SDs = n.sd;
     g_net_forward(n, w.theta, w.xs, SDs, B, w.actA, sm);    // q_values = model(states)            (activations kept)
     g_q_values(n, w.actA, B, w.q, red);
@@ -511,7 +511,7 @@ __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars&
 }
 
 // greedy action of ONE state row (select_train/test_action); result uniform across the CTA
-__device__ int g_greedy_row(const GNet& n, const GSlot& w, const float* state_row /* [sd] in global memory */, float* sm, float* red,
+static __device__ int g_greedy_row(const GNet& n, const GSlot& w, const float* state_row /* [sd] in global memory */, float* sm, float* red,
                             int* ibox) {
     g_net_forward(n, w.theta, state_row, n.sd, 1, w.actB, sm);
     g_q_values(n, w.actB, 1, w.q2, red);
@@ -561,7 +561,7 @@ __device__ inline GSlot gslot_view(float* base, const GNet& n, int ring_cap, int
 }
 
 // torch default nn.Linear init of a general net from the P_QINIT stream (same stream as the CPU restatement)
-__device__ void g_init_layer(const GLayer& l, float* th, uint32_t k0, uint32_t k1) {
+static __device__ void g_init_layer(const GLayer& l, float* th, uint32_t k0, uint32_t k1) {
     const double bnd = 1.0 / sqrt((double)l.in);
     const int end = l.b_off + l.out;
     for (int p = l.w_off + threadIdx.x; p < end; p += kGThreads) {

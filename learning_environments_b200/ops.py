@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import LaneCfg, LaneOut, Trace, check
+from ._abi import LaneCfg, LaneOut, Td3Cfg, Trace, check
 
 _F32, _I32, _F64 = torch.float32, torch.int32, torch.float64
 
@@ -262,3 +262,49 @@ def nes_partial_update(P, member_lo, member_hi, seed, generation, noise_std, coe
                                        C.c_uint32(generation), C.c_float(noise_std), _ptr(_dev(coef, _F32)), _ptr(_dev(sign, _F32)),
                                        _stream()), "le_nes_partial_update")
     return delta
+
+
+# ---------------------------------------------------------------------------------------------------------
+def td3_param_counts(tcfg):
+    a, c = C.c_int(), C.c_int()
+    check(_lib().le_td3_param_counts(C.byref(tcfg), C.byref(a), C.byref(c)), "le_td3_param_counts")
+    return a.value, c.value
+
+
+def td3_run_host(tcfg, env_theta, env_index, keys, actor_init, critic1_init, critic2_init, trace_cap=0, trace_lane=0, device=0):
+    """le_td3_run_host: n TD3_discrete_vary lanes (train with per-episode test + final test), HOST numpy buffers in and out.
+    actor_init [1 or n, P_actor], critic*_init [1 or n, P_critic].  Returns a dict of arrays (+ 'trace' when trace_cap > 0)."""
+    assert isinstance(tcfg, Td3Cfg)
+    c = tcfg.base
+    keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint32).reshape(-1, 2))
+    n = keys.shape[0]
+    Pa, Pc = td3_param_counts(tcfg)
+    a0 = np.ascontiguousarray(actor_init, np.float32).reshape(-1, Pa)
+    q1 = np.ascontiguousarray(critic1_init, np.float32).reshape(-1, Pc)
+    q2 = np.ascontiguousarray(critic2_init, np.float32).reshape(-1, Pc)
+    assert a0.shape[0] == q1.shape[0] == q2.shape[0] and a0.shape[0] in (1, n)
+    th, n_env = None, 0
+    if env_theta is not None:
+        th = np.ascontiguousarray(env_theta, np.float32).reshape(-1, c.env_params())
+        n_env = th.shape[0]
+    ei = None if env_index is None else np.ascontiguousarray(env_index, np.int32)
+    af = np.zeros((n, Pa), np.float32)
+    out = np.zeros(n, dtype=lane_out_dtype())
+    rs = max(c.train_episodes, 1)
+    rewards, lengths = np.zeros((n, rs), np.float64), np.zeros((n, rs), np.int32)
+    test_rewards = np.zeros((n, c.test_episodes), np.float64)
+    tr, trace = None, None
+    if trace_cap > 0:
+        trace = dict(action=np.zeros(trace_cap, np.int32), explore=np.zeros(trace_cap, np.int32), next_state=np.zeros((trace_cap, c.sd), np.float32),
+                     reward=np.zeros(trace_cap, np.float32), done=np.zeros(trace_cap, np.float32), loss=np.zeros(trace_cap, np.float32))
+        tr = Trace()
+        tr.cap = trace_cap
+        for k, v in trace.items():
+            setattr(tr, k, v.ctypes.data)
+
+    def p(a):
+        return a.ctypes.data_as(C.c_void_p) if a is not None else None
+    check(_lib().le_td3_run_host(C.byref(tcfg), p(th), C.c_int(n_env), p(ei), p(keys), p(a0), p(q1), p(q2), C.c_int(a0.shape[0]), p(af),
+                                 C.c_int(n), p(out), p(rewards), p(lengths), p(test_rewards), C.byref(tr) if tr is not None else None,
+                                 C.c_int(trace_lane), C.c_int(device)), "le_td3_run_host")
+    return dict(out=out, rewards=rewards, lengths=lengths, test_rewards=test_rewards, actor_final=af, trace=trace)

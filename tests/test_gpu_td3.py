@@ -1,0 +1,59 @@
+"""GPU parity tests of the TD3_discrete_vary lanes: the CUDA path through le_td3_run_host against the
+reference's own trajectory (golden from the unmodified reference under RNG injection) and against the CPU restatement."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, philox
+from tests.helpers import cfg_from_bytes, load_golden, rel_err, sync_prefix
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfgs(g):
+    from learning_environments_b200._abi import Td3Cfg
+    import ctypes as C
+    base = cfg_from_bytes(g["cfg"])
+    ocfg = c_oracle.td3_cfg(base, json.loads(str(g["agent_cfg_json"])), float(g["max_action"]))
+    t = Td3Cfg()
+    assert C.sizeof(t) == C.sizeof(ocfg)
+    C.memmove(C.byref(t), C.byref(ocfg), C.sizeof(t))        # the two structs have the same layout
+    return t, ocfg
+
+
+def test_td3_trajectory_lockstep_vs_reference_golden():
+    from learning_environments_b200 import ops
+    g = load_golden("trajectory_td3_cartpole_se.npz")
+    tcfg, _ = _cfgs(g)
+    cap = len(g["action"])
+    res = ops.td3_run_host(tcfg, g["env_theta"], None, [tuple(int(k) for k in g["key"])], g["init_actor"], g["init_critic_1"],
+                           g["init_critic_2"], trace_cap=cap)
+    tr = res["trace"]
+    n = sync_prefix(g["action"], tr["action"])
+    assert n >= min(cap, 250), "kernel left the reference trajectory after %d steps" % n     # 200 init steps + >= 50 learning steps
+    assert rel_err(tr["next_state"][:n], g["next_state"][:n], 1e-2) < 2e-4
+    assert rel_err(tr["reward"][:n], g["reward"][:n], 1e-2) < 2e-4
+    assert np.array_equal(tr["done"][:n] > 0.5, g["done"][:n] > 0.5)
+    assert np.array_equal(np.isnan(tr["loss"][:n]), np.arange(n) < 200)                        # learn() from the second episode on
+    out = res["out"][0]
+    if n == cap and int(out["train_steps"]) == int(g["train_steps"]):
+        assert int(out["learn_iters"]) == int(g["learn_iters"])
+        assert np.array_equal(res["lengths"][0, :len(g["lengths"])], g["lengths"])
+
+
+def test_td3_lanes_vs_cpu_restatement():
+    from learning_environments_b200 import ops
+    g = load_golden("trajectory_td3_cartpole_se.npz")
+    tcfg, ocfg = _cfgs(g)
+    for t in (tcfg, ocfg):
+        t.base.train_episodes, t.base.test_episodes = 3, 3
+    keys = [philox.lane_key(51, 0, i, 0, 0) for i in range(5)]
+    res = ops.td3_run_host(tcfg, g["env_theta"], None, keys, g["init_actor"], g["init_critic_1"], g["init_critic_2"])
+    same = 0
+    for i, k in enumerate(keys):
+        want = c_oracle.run_lane_td3(ocfg, g["env_theta"], k, g["init_actor"], g["init_critic_1"], g["init_critic_2"])
+        assert res["lengths"][i, 0] == want["lengths"][0]                  # init episode: random actions, exact
+        same += int(res["out"][i]["train_steps"] == want["train_steps"] and res["out"][i]["n_episodes"] == want["n_episodes"])
+    assert same >= 3
+    assert np.isfinite(res["actor_final"]).all() and np.isfinite(res["out"]["score"]).all()
