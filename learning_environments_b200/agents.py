@@ -369,8 +369,145 @@ class DuelingDDQN_vary(DuelingDDQN):
         super().__init__(env=env, config=config_mod, icm=icm)
 
 
+class Actor_TD3_discrete(nn.Module):
+    """models/actor_critic.py:22-36: MLP * max_action -> F.gumbel_softmax(tau, hard)."""
+
+    def __init__(self, state_dim, action_dim, max_action, agent_name, config):
+        super().__init__()
+        c = config["agents"][agent_name]
+        self.net = build_nn_from_config(input_dim=state_dim, output_dim=action_dim, nn_config=c)
+        self.max_action = max_action
+        self.gumbel_softmax_temp = c["gumbel_softmax_temp"]
+        self.gumbel_softmax_hard = c["gumbel_softmax_hard"]
+
+    def forward(self, state, tau):
+        return torch.nn.functional.gumbel_softmax(self.net(state) * self.max_action, tau=tau, hard=self.gumbel_softmax_hard)
+
+
+class Critic_Q(nn.Module):
+    """models/actor_critic.py:69-76."""
+
+    def __init__(self, state_dim, action_dim, agent_name, config):
+        super().__init__()
+        self.net = build_nn_from_config(input_dim=state_dim + action_dim, output_dim=1, nn_config=config["agents"][agent_name])
+
+    def forward(self, state, action):
+        return self.net(torch.cat([state, action], dim=len(state.shape) - 1))
+
+
+class TD3_discrete_vary(BaseAgent):
+    """agents/TD3_discrete_vary.py: TD3 with a Gumbel-softmax actor for discrete action spaces.  train() / test() run as
+    one lane of the TD3 kernel (le_td3_run_host); the nets below hold the torch-default initial weights and receive the
+    trained actor back."""
+
+    def __init__(self, env, min_action, max_action, config):
+        self.agent_name = 'td3_discrete_vary'
+        if config["agents"][self.agent_name]["vary_hp"]:
+            config = copy.deepcopy(config)
+            a = vary_hyperparameters(config["agents"][self.agent_name], _VARY_RNG)
+            a["hidden_layer"] = max(a["hidden_layer"], 1)
+            config["agents"][self.agent_name] = a
+        super().__init__(agent_name=self.agent_name, env=env, config=config)
+        c = config["agents"][self.agent_name]
+        self.full_config = config
+        self.max_action, self.min_action = max_action, min_action
+        for k in ("batch_size", "rb_size", "gamma", "tau", "policy_delay", "lr", "action_std", "policy_std", "policy_std_clip"):
+            setattr(self, k, c[k])
+        if str(c["activation_fn"]) not in ("tanh", "relu", "leakyrelu") or int(c["hidden_layer"]) > 3:
+            raise NotImplementedError("TD3 nets with activation %r / hidden_layer %r are outside the compiled kernel set"
+                                      % (c["activation_fn"], c["hidden_layer"]))
+        _cuda_device()
+        self.actor = Actor_TD3_discrete(self.state_dim, self.action_dim, max_action, self.agent_name, config)
+        self.actor_target = copy.deepcopy(self.actor)
+        self.critic_1 = Critic_Q(self.state_dim, self.action_dim, self.agent_name, config)
+        self.critic_2 = Critic_Q(self.state_dim, self.action_dim, self.agent_name, config)
+        self.critic_target_1, self.critic_target_2 = copy.deepcopy(self.critic_1), copy.deepcopy(self.critic_2)
+        self.total_it = 0
+        self.gumbel_temp_anneal_steps = np.linspace(self.actor.gumbel_softmax_temp, self.actor.gumbel_softmax_temp / 20, 2000)
+        self.gumbel_temp_annealed = self.gumbel_temp_anneal_steps[0]
+        self._env_name = config["env_name"]
+        self._cfg_section = c
+        self._seed = random.getrandbits(32)
+        self._runs = 0
+        self.step_budget = 0
+
+    def _td3_cfg(self, env, test_env, train_episodes, final_test, time_remaining):
+        from ._abi import Td3Cfg
+        from .envs import linear_theta
+        kind, theta, fields = env.kernel_env() if isinstance(env, EnvWrapper) else (ENV_REAL, None, {})
+        t = Td3Cfg()
+        c, a = t.base, self._cfg_section
+        c.sd, c.ad, c.env_kind, c.real_env = self.state_dim, self.action_dim, kind, REAL_ENV_IDS[self._env_name]
+        c.env_hidden, c.env_act = int(fields.get("env_hidden", 0)), int(fields.get("env_act", ACT_IDS["identity"]))
+        for i, sl in enumerate(fields.get("env_slope", [0.01] * 3)):
+            c.env_slope[i] = sl
+        c.q_hidden, c.q_layers, c.q_act = int(a["hidden_size"]), max(int(a["hidden_layer"]), 1), ACT_IDS[str(a["activation_fn"])]
+        c.batch_size, c.rb_size = int(self.batch_size), int(self.rb_size)
+        c.train_episodes, c.test_episodes, c.init_episodes = int(train_episodes), int(self.test_episodes), int(self.init_episodes)
+        c.max_steps, c.early_out_num = int(env.max_episode_steps()), int(self.early_out_num)
+        c.same_action_num = max(int(self.same_action_num), 1)
+        c.use_test_env, c.final_test = (1 if test_env is not None else 0), (1 if final_test else 0)
+        budget = int(self.step_budget)
+        if time_remaining < 1e8:
+            tb = max(int(time_remaining * STEPS_PER_SECOND), 1)
+            budget = tb if budget == 0 else min(budget, tb)
+        c.step_budget = budget
+        c.gamma, c.lr, c.tau = float(self.gamma), float(self.lr), float(self.tau)
+        c.early_out_virtual_diff = float(self.early_out_virtual_diff)
+        c.solved_reward = float((test_env if test_env is not None else env).get_solved_reward())
+        c.beta1, c.beta2, c.adam_eps = 0.9, 0.999, 1e-8
+        t.policy_delay, t.gumbel_hard = int(self.policy_delay), int(bool(self.actor.gumbel_softmax_hard))
+        t.action_std, t.policy_std, t.policy_std_clip = float(self.action_std), float(self.policy_std), float(self.policy_std_clip)
+        t.gumbel_temp, t.max_action = float(self.actor.gumbel_softmax_temp), float(self.max_action)
+        nets = [linear_theta(m).numpy() for m in (self.actor, self.critic_1, self.critic_2)]
+        return t, (None if theta is None else theta.numpy()), nets
+
+    def _run(self, t, theta, nets):
+        key = lane_keys(self._seed, self._runs, [0], [0], [0])
+        self._runs += 1
+        return ops.td3_run_host(t, theta, None, key, nets[0], nets[1], nets[2], device=torch.cuda.current_device())
+
+    def train(self, env, test_env=None, time_remaining=1e9):
+        """agents/base_agent.py:64-153 with the TD3 act / learn as one lane of the TD3 kernel (fresh targets / optimizers)."""
+        from .envs import set_linear_theta
+        env.set_agent_params(same_action_num=self.same_action_num, gamma=self.gamma)
+        t, theta, nets = self._td3_cfg(env, test_env, self.train_episodes, False, time_remaining)
+        res = self._run(t, theta, nets)
+        out = res["out"][0]
+        n = int(out["n_episodes"])
+        rewards, lengths = res["rewards"][0, :n].tolist(), res["lengths"][0, :n].tolist()
+        if int(out["timed_out"]):
+            print("timeout")
+            rewards = rewards or [-1e9]
+            lengths = lengths or [1e9]
+            rewards += [min(rewards)] * (self.train_episodes - len(rewards))
+            lengths += [max(lengths)] * (self.train_episodes - len(lengths))
+        set_linear_theta(self.actor, torch.from_numpy(res["actor_final"][0]))
+        self.total_it += int(out["learn_iters"])
+        if self.total_it > 0:
+            self.gumbel_temp_annealed = self.gumbel_temp_anneal_steps[min(self.total_it, 2000) - 1]
+        env.close()
+        return rewards, lengths, ReplayBuffer(state_dim=self.state_dim, action_dim=self.action_dim, device=self.device,
+                                              max_size=int(self.rb_size))
+
+    def test(self, env, time_remaining=1e9):
+        """agents/base_agent.py:155-227 with select_test_action (:164-166) at the current (annealed) Gumbel temperature."""
+        if isinstance(env, EnvWrapper) and env.is_virtual_env():
+            raise NotImplementedError("test() on a synthetic env is outside the hot path (the reference tests on the real env)")
+        env.set_agent_params(same_action_num=self.same_action_num, gamma=self.gamma)
+        t, _, nets = self._td3_cfg(env, None, 0, True, 1e9)
+        t.base.env_kind = ENV_REAL
+        t.gumbel_temp = float(self.gumbel_temp_annealed)
+        res = self._run(t, None, nets)
+        env.close()
+        return res["test_rewards"][0].tolist(), [], ReplayBuffer(state_dim=self.state_dim, action_dim=self.action_dim,
+                                                                  device=self.device, max_size=int(1e6))
+
+
+_VARY_RNG = np.random.RandomState()
+
 _OUTSIDE_HOT_PATH = {"td3", "td3_icm", "td3_vary", "td3_icm_vary", "ppo", "ppo_icm", "duelingddqn_icm",
-                     "duelingddqn_icm_vary", "td3_discrete_vary", "ql", "ql_cb", "sarsa", "sarsa_cb", "ddqn_icm", "ddqn_icm_vary"}
+                     "duelingddqn_icm_vary", "ql", "ql_cb", "sarsa", "sarsa_cb", "ddqn_icm", "ddqn_icm_vary"}
 
 
 def select_agent(config, agent_name):
@@ -386,6 +523,8 @@ def select_agent(config, agent_name):
         return DuelingDDQN(env=dummy_env, config=config)
     if agent_name == "duelingddqn_vary":
         return DuelingDDQN_vary(env=dummy_env, config=config)
+    if agent_name == "td3_discrete_vary":
+        return TD3_discrete_vary(env=dummy_env, config=config, min_action=dummy_env.get_min_action(), max_action=dummy_env.get_max_action())
     if agent_name in _OUTSIDE_HOT_PATH:
-        raise NotImplementedError("RL agent %r is outside the B200 hot path (DDQN / DDQN_vary are built)" % agent_name)
+        raise NotImplementedError("RL agent %r is outside the B200 hot path (DDQN / DuelingDDQN / TD3_discrete_vary families are built)" % agent_name)
     raise NotImplementedError("Unknownn RL agent")

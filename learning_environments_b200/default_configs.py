@@ -30,6 +30,12 @@ _CARTPOLE_SE = {
                             activation_fn="tanh", hidden_size=61, hidden_layer=1, feature_dim=60, print_rate=1, early_out_num=1,
                             early_out_virtual_diff=0.01),
         "duelingddqn_vary": dict(vary_hp=True),
+        # default_config_cartpole_syn_env.yaml:79-101
+        "td3_discrete_vary": dict(train_episodes=1000, test_episodes=10, init_episodes=1, batch_size=122, gamma=0.9989, lr=0.0017496,
+                               tau=0.0724303, policy_delay=1, rb_size=1000000, same_action_num=1, activation_fn="tanh", hidden_size=510,
+                               hidden_layer=2, action_std=0.037275, policy_std=0.2225286, policy_std_clip=0.5, print_rate=1,
+                               early_out_num=1, early_out_virtual_diff=0.01, gumbel_softmax_temp=2.3076235, gumbel_softmax_hard=True,
+                               vary_hp=False),
     },
     "envs": {"CartPole-v0": dict(solved_reward=195.0, max_steps=200, activation_fn="leakyrelu", hidden_size=83,
                                  hidden_layer=1, info_dim=0, reward_env_type=0)},
@@ -50,6 +56,12 @@ _ACROBOT_SE = {
                             hidden_size=128, hidden_layer=2, feature_dim=128, print_rate=1, early_out_num=10,
                             early_out_virtual_diff=0.01),
         "duelingddqn_vary": dict(vary_hp=True),
+        # default_config_acrobot_syn_env.yaml:58-80
+        "td3_discrete_vary": dict(train_episodes=1000, test_episodes=10, init_episodes=1, batch_size=122, gamma=0.9989, lr=0.0017496,
+                               tau=0.0724303, policy_delay=1, rb_size=1000000, same_action_num=1, activation_fn="tanh", hidden_size=510,
+                               hidden_layer=2, action_std=0.037275, policy_std=0.2225286, policy_std_clip=0.5, print_rate=1,
+                               early_out_num=1, early_out_virtual_diff=0.01, gumbel_softmax_temp=2.3076235, gumbel_softmax_hard=True,
+                               vary_hp=False),
     },
     "envs": {"Acrobot-v1": dict(solved_reward=-100.0, max_steps=500, activation_fn="prelu", hidden_size=167,
                                 hidden_layer=1, info_dim=0, reward_env_type=0)},

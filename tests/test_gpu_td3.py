@@ -57,3 +57,22 @@ def test_td3_lanes_vs_cpu_restatement():
         same += int(res["out"][i]["train_steps"] == want["train_steps"] and res["out"][i]["n_episodes"] == want["n_episodes"])
     assert same >= 3
     assert np.isfinite(res["actor_final"]).all() and np.isfinite(res["out"]["score"]).all()
+
+
+def test_td3_agent_class_train_and_test_like_the_reference_api():
+    """select_agent(config, 'td3_discrete_vary') -> agent.train(env, test_env) / agent.test(env) (agents/agent_utils.py:53-56)."""
+    import torch
+    from learning_environments_b200 import agents, default_configs, envs
+    cfg = default_configs.get("cartpole_syn_env")
+    cfg["agents"]["td3_discrete_vary"].update(train_episodes=3, test_episodes=2, init_episodes=1, hidden_size=24, batch_size=16)
+    torch.manual_seed(4)
+    fac = envs.EnvFactory(cfg)
+    venv, real = fac.generate_virtual_env(), fac.generate_real_env()
+    agent = agents.select_agent(cfg, "td3_discrete_vary")
+    before = envs.linear_theta(agent.actor).clone()
+    rewards, lengths, _ = agent.train(env=venv, test_env=real)
+    assert 1 <= len(rewards) == len(lengths) <= 3 and all(np.isfinite(r) and r > 0 for r in rewards)
+    assert agent.total_it == sum(lengths[1:]) and agent.gumbel_temp_annealed < agent.gumbel_temp_anneal_steps[0]
+    assert not torch.equal(before, envs.linear_theta(agent.actor))           # the trained actor came back
+    test_rewards, _, _ = agent.test(env=real)
+    assert len(test_rewards) == 2 and all(1.0 <= r <= 200.0 for r in test_rewards)
