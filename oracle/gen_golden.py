@@ -160,13 +160,14 @@ def gen_td_update(yaml_name, tag, seed, steps=5, agent=None, **overrides):
              cfg=cfg_bytes(cfg, agent_name, ENV_RN if "reward_env" in yaml_name else ENV_SE))
 
 
-def gen_td3_learn(seed, steps=5):
+def gen_td3_learn(seed, steps=5, tag="cartpole", yaml_name="default_config_cartpole_syn_env.yaml", **overrides):
     """TD3_discrete_vary.learn (agents/TD3_discrete_vary.py:62-119) `steps` times on explicit minibatches with the random
     draws (policy noise randn_like, the exponential_() of both gumbel_softmax calls) logged: groundwork for SURVEY §8(f) rank 2."""
     import torch
     mods = rh.import_reference()
-    cfg, agent_name = small_config("default_config_cartpole_syn_env.yaml", "td3_discrete_vary", hidden_size=24, hidden_layer=2,
-                                   batch_size=16, policy_delay=2, vary_hp=False)
+    kw = dict(hidden_size=24, hidden_layer=2, batch_size=16, policy_delay=2, vary_hp=False)
+    kw.update(overrides)
+    cfg, agent_name = small_config(yaml_name, "td3_discrete_vary", **kw)
     torch.manual_seed(seed)
     agent = mods["agents.agent_utils"].select_agent(cfg, "td3_discrete_vary")
     sd, ad, B = agent.state_dim, agent.action_dim, agent.batch_size
@@ -226,7 +227,8 @@ def gen_td3_learn(seed, steps=5):
         expo_target.append(log["expo"][i]); i += 1
         expo_actor.append(log["expo"][i] if u else np.zeros((B, ad), np.float32)); i += u
     a = cfg["agents"]["td3_discrete_vary"]
-    np.savez(os.path.join(GOLDEN, "td3_learn_cartpole.npz"), sd=sd, ad=ad, hidden=a["hidden_size"], layers=a["hidden_layer"],
+    np.savez(os.path.join(GOLDEN, "td3_learn_%s.npz" % tag), sd=sd, ad=ad, hidden=a["hidden_size"], layers=a["hidden_layer"],
+             act=le_config.ACT_IDS[str(a["activation_fn"])],
              gamma=a["gamma"], tau=a["tau"], lr=a["lr"], policy_delay=a["policy_delay"], policy_std=a["policy_std"],
              policy_std_clip=a["policy_std_clip"], gumbel_hard=int(a["gumbel_softmax_hard"]), max_action=float(agent.max_action),
              temps=np.array(temps, np.float64), updated=np.array(updated, np.int32), rows=rows, policy_noise=np.stack(log["randn"]),
@@ -477,6 +479,11 @@ def main():
         ("td_update_acrobot_dueling", lambda: gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")),
         ("td_update_cartpole_ddqn_l2", lambda: gen_td_update(CP, "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)),
         ("td3_learn_cartpole", lambda: gen_td3_learn(41)),
+        # soft Gumbel-softmax, relu nets, one hidden layer, policy update on every call; Acrobot shapes (sd 6, ad 3) with leakyrelu
+        ("td3_learn_cartpole_soft", lambda: gen_td3_learn(43, tag="cartpole_soft", gumbel_softmax_hard=False, activation_fn="relu",
+                                                          hidden_layer=1, policy_delay=1)),
+        ("td3_learn_acrobot", lambda: gen_td3_learn(44, tag="acrobot", yaml_name="default_config_acrobot_syn_env.yaml",
+                                                    activation_fn="leakyrelu", policy_delay=3, steps=7)),
         ("trajectory_td3_cartpole_se", lambda: gen_trajectory_td3("cartpole_se", 42, (0x81, 0x82),
                                                                   dict(train_episodes=4, test_episodes=2, init_episodes=1, hidden_size=24,
                                                                        hidden_layer=2, batch_size=16, policy_delay=2, vary_hp=False),

@@ -109,10 +109,12 @@ def test_trajectory_lockstep(tag):
         assert np.allclose(res["rewards"], g["rewards"], rtol=1e-4, atol=1e-4)
 
 
-def test_td3_discrete_learn_restatement_vs_reference_golden():
-    """Groundwork for SURVEY §8(f) rank 2: TD3_discrete_vary.learn (agents/TD3_discrete_vary.py:62-119: Gumbel-softmax actor,
-    twin critics, delayed policy update) restated in C and held to five learn() calls of the unmodified reference."""
-    g = load_golden("td3_learn_cartpole.npz")
+@pytest.mark.parametrize("tag", ["cartpole", "cartpole_soft", "acrobot"])
+def test_td3_discrete_learn_restatement_vs_reference_golden(tag):
+    """TD3_discrete_vary.learn (agents/TD3_discrete_vary.py:62-119: Gumbel-softmax actor, twin critics,
+    delayed policy update) restated in C and held to learn() calls of the unmodified reference — hard and soft Gumbel-softmax,
+    tanh / relu / leakyrelu nets, one and two hidden layers, policy_delay 1 / 2 / 3, CartPole and Acrobot shapes."""
+    g = load_golden("td3_learn_%s.npz" % tag)
     names = ("actor", "actor_target", "critic_1", "critic_target_1", "critic_2", "critic_target_2")
     nets = {n: g["init_" + n].astype(np.float32).copy() for n in names}
     Pa, Pc = nets["actor"].size, nets["critic_1"].size
@@ -121,7 +123,7 @@ def test_td3_discrete_learn_restatement_vs_reference_golden():
     hyper = dict(gamma=float(g["gamma"]), tau=float(g["tau"]), lr=float(g["lr"]), policy_delay=int(g["policy_delay"]),
                  max_action=float(g["max_action"]), policy_std=float(g["policy_std"]), policy_std_clip=float(g["policy_std_clip"]),
                  gumbel_hard=int(g["gumbel_hard"]))
-    dims = (int(g["sd"]), int(g["ad"]), int(g["hidden"]), int(g["layers"]), 0)      # activation_fn tanh
+    dims = (int(g["sd"]), int(g["ad"]), int(g["hidden"]), int(g["layers"]), int(g["act"]))
     counters = [0, 0]
     for k in range(len(g["temps"])):
         closs, aloss = c_oracle.td3_learn(dims, hyper, nets, adam, counters, k + 1, g["rows"][k], g["policy_noise"][k],
@@ -129,7 +131,7 @@ def test_td3_discrete_learn_restatement_vs_reference_golden():
         assert np.isfinite(closs) and (np.isfinite(aloss) == bool(g["updated"][k]))
         for n in names:
             err = np.abs(nets[n] - g["after_" + n][k]).max()      # weights move by ~lr = 1.7e-3 per step; observed error ~1 ulp
-            assert err < 1e-6, (k, n, err)
+            assert err < 1e-6, (tag, k, n, err)
     assert counters == [int(g["updated"].sum()), len(g["temps"])]
 
 
