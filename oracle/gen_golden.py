@@ -344,21 +344,26 @@ def gen_trajectory(yaml_name, tag, seed, key, env_kind, overrides, trace_cap, us
           rewards[:4], "test", test_rewards[:3])
 
 
-def gen_trajectory_td3(tag, seed, key, overrides, trace_cap):
+def gen_trajectory_td3(tag, seed, key, overrides, trace_cap, yaml_name="default_config_cartpole_syn_env.yaml", env_kind="se"):
     """BaseAgent.train (+ per-episode test) and test of the reference's TD3_discrete_vary on a CartPole SE under RNG injection
     (oracle/ref_harness.py Td3RngInjector): groundwork for SURVEY §8(f) rank 2."""
     import torch
     mods = rh.import_reference()
-    yaml_name = "default_config_cartpole_syn_env.yaml"
     cfg, agent_name = small_config(yaml_name, "td3_discrete_vary", **overrides)
     torch.manual_seed(seed)
     fac = mods["envs.env_factory"].EnvFactory(cfg)
     real_env = fac.generate_real_env()
-    train_env = fac.generate_virtual_env()
-    env_theta = linear_params(train_env)
+    if env_kind == "se":
+        train_env = fac.generate_virtual_env()
+        env_theta = linear_params(train_env)
+        reset_envs = [train_env.env.reset_env.env.unwrapped, real_env.env.unwrapped]
+    else:
+        train_env = fac.generate_real_env()
+        env_theta = np.zeros(1, np.float32)
+        reset_envs = [train_env.env.unwrapped, real_env.env.unwrapped]
     agent = mods["agents.agent_utils"].select_agent(cfg, "td3_discrete_vary")
     init = {n: linear_params(getattr(agent, n)) for n in ("actor", "critic_1", "critic_2")}
-    inj = rh.Td3RngInjector(key, agent.action_dim, "cartpole")
+    inj = rh.Td3RngInjector(key, agent.action_dim, "cartpole" if "CartPole" in cfg["env_name"] else "acrobot")
     tr = dict(action=[], next_state=[], reward=[], done=[])
     orig_step = train_env.step
 
@@ -371,14 +376,13 @@ def gen_trajectory_td3(tag, seed, key, overrides, trace_cap):
         return s2, r, d
 
     train_env.step = step
-    with rh.injected_rng_td3(inj, agent, reset_envs=[train_env.env.reset_env.env.unwrapped, real_env.env.unwrapped],
-                             action_spaces=[train_env.env.action_space]):
+    with rh.injected_rng_td3(inj, agent, reset_envs=reset_envs, action_spaces=[train_env.env.action_space]):
         rewards, lengths, _ = agent.train(env=train_env, test_env=real_env)
         test_rewards, _, _ = agent.test(env=real_env)
     n = min(trace_cap, len(tr["action"]))
     a = cfg["agents"]["td3_discrete_vary"]
     np.savez(os.path.join(GOLDEN, "trajectory_td3_%s.npz" % tag), key=np.array(key, np.uint32),
-             cfg=cfg_bytes_td3(cfg), agent_cfg_json=np.array(__import__("json").dumps(a)), max_action=float(agent.max_action),
+             cfg=cfg_bytes_td3(cfg, ENV_SE if env_kind == "se" else ENV_REAL), agent_cfg_json=np.array(__import__("json").dumps(a)), max_action=float(agent.max_action),
              env_theta=env_theta, init_actor=init["actor"], init_critic_1=init["critic_1"], init_critic_2=init["critic_2"],
              actor_final=linear_params(agent.actor), rewards=np.array(rewards, np.float64), lengths=np.array(lengths, np.int32),
              test_rewards=np.array(test_rewards, np.float64), train_steps=len(tr["action"]), learn_iters=inj.learn_iters,
@@ -388,7 +392,7 @@ def gen_trajectory_td3(tag, seed, key, overrides, trace_cap):
           "test", test_rewards[:3])
 
 
-def cfg_bytes_td3(cfg):
+def cfg_bytes_td3(cfg, env_kind=ENV_SE):
     """le_lane_cfg bytes for a TD3 lane: env / loop fields from the ddqn-style mapping, MLP shape from the td3 section."""
     d = copy.deepcopy(cfg)
     a = d["agents"]["td3_discrete_vary"]
@@ -397,7 +401,7 @@ def cfg_bytes_td3(cfg):
               "activation_fn", "hidden_size", "hidden_layer", "early_out_num", "early_out_virtual_diff"):
         ddqn_like[k] = a[k]
     d["agents"]["ddqn"] = ddqn_like
-    c = le_config.lane_cfg(d, agent_name="ddqn", env_kind=ENV_SE, use_test_env=True, final_test=True)
+    c = le_config.lane_cfg(d, agent_name="ddqn", env_kind=env_kind, use_test_env=True, final_test=True)
     return np.frombuffer(bytes(c), dtype=np.uint8).copy()
 
 
@@ -488,6 +492,15 @@ def main():
                                                                   dict(train_episodes=4, test_episodes=2, init_episodes=1, hidden_size=24,
                                                                        hidden_layer=2, batch_size=16, policy_delay=2, vary_hp=False),
                                                                   trace_cap=400)),
+        ("trajectory_td3_acrobot_se", lambda: gen_trajectory_td3("acrobot_se", 45, (0x83, 0x84),
+                                                                 dict(train_episodes=2, test_episodes=1, init_episodes=1, hidden_size=20,
+                                                                      hidden_layer=1, batch_size=12, policy_delay=1, vary_hp=False,
+                                                                      activation_fn="relu"), trace_cap=700,
+                                                                 yaml_name="default_config_acrobot_syn_env.yaml")),
+        ("trajectory_td3_cartpole_real", lambda: gen_trajectory_td3("cartpole_real", 46, (0x85, 0x86),
+                                                                    dict(train_episodes=12, test_episodes=2, init_episodes=2, hidden_size=24,
+                                                                         hidden_layer=2, batch_size=16, policy_delay=2, vary_hp=False,
+                                                                         same_action_num=2), trace_cap=300, env_kind="real")),
         ("real_env", lambda: gen_real_env(7)),
         ("trajectory_cartpole_se", lambda: gen_trajectory(CP, "cartpole_se", 11, (0x1234, 0xABCD), "se",
                                                           dict(train_episodes=5, test_episodes=3, init_episodes=1), trace_cap=400)),
