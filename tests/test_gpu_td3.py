@@ -22,20 +22,22 @@ def _cfgs(g):
     return t, ocfg
 
 
-def test_td3_trajectory_lockstep_vs_reference_golden():
+@pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_real"])
+def test_td3_trajectory_lockstep_vs_reference_golden(tag):
     from learning_environments_b200 import ops
-    g = load_golden("trajectory_td3_cartpole_se.npz")
+    g = load_golden("trajectory_td3_%s.npz" % tag)
     tcfg, _ = _cfgs(g)
     cap = len(g["action"])
-    res = ops.td3_run_host(tcfg, g["env_theta"], None, [tuple(int(k) for k in g["key"])], g["init_actor"], g["init_critic_1"],
-                           g["init_critic_2"], trace_cap=cap)
+    n_init = int(g["lengths"][:tcfg.base.init_episodes].sum()) // max(tcfg.base.same_action_num, 1)     # agent steps before learn() starts
+    res = ops.td3_run_host(tcfg, g["env_theta"] if tcfg.base.env_kind == 0 else None, None, [tuple(int(k) for k in g["key"])],
+                           g["init_actor"], g["init_critic_1"], g["init_critic_2"], trace_cap=cap)
     tr = res["trace"]
     n = sync_prefix(g["action"], tr["action"])
-    assert n >= min(cap, 250), "kernel left the reference trajectory after %d steps" % n     # 200 init steps + >= 50 learning steps
+    assert n >= min(cap, n_init + 50), "kernel left the reference trajectory after %d steps" % n
     assert rel_err(tr["next_state"][:n], g["next_state"][:n], 1e-2) < 2e-4
     assert rel_err(tr["reward"][:n], g["reward"][:n], 1e-2) < 2e-4
     assert np.array_equal(tr["done"][:n] > 0.5, g["done"][:n] > 0.5)
-    assert np.array_equal(np.isnan(tr["loss"][:n]), np.arange(n) < 200)                        # learn() from the second episode on
+    assert np.array_equal(np.isnan(tr["loss"][:n]), np.arange(n) < n_init)                     # learn() after the init episodes
     out = res["out"][0]
     if n == cap and int(out["train_steps"]) == int(g["train_steps"]):
         assert int(out["learn_iters"]) == int(g["learn_iters"])
