@@ -46,3 +46,20 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/philox.py", "").replace("oracle/le_oracle.c", ""), \
                     "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_td3_cfg_layout_is_shared_by_the_binding_and_the_restatement():
+    """struct le_td3_cfg (include/le_b200.h) == learning_environments_b200._abi.Td3Cfg == oracle.c_oracle.Td3Cfg field by field,
+    and le_td3_param_counts (no GPU needed) agrees with the restatement's parameter counts."""
+    from oracle import c_oracle
+    a, b = _abi.Td3Cfg, c_oracle.Td3Cfg
+    assert C.sizeof(a) == C.sizeof(b) == C.sizeof(_abi.LaneCfg) + 48
+    assert [(n, getattr(a, n).offset) for n, _ in a._fields_] == [(n, getattr(b, n).offset) for n, _ in b._fields_]
+    lib = _abi.load_library()
+    t = _abi.Td3Cfg()
+    t.base.sd, t.base.ad, t.base.q_hidden, t.base.q_layers = 6, 3, 20, 1
+    pa, pc = C.c_int(), C.c_int()
+    assert lib.le_td3_param_counts(C.byref(t), C.byref(pa), C.byref(pc)) == 0
+    oa, oc = C.c_int(), C.c_int()
+    c_oracle.lib().le_oracle_td3_params(C.c_int(6), C.c_int(3), C.c_int(20), C.c_int(1), C.byref(oa), C.byref(oc))
+    assert (pa.value, pc.value) == (oa.value, oc.value) == (6 * 20 + 20 + 20 * 3 + 3, 9 * 20 + 20 + 20 + 1)
