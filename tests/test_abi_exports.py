@@ -63,3 +63,20 @@ def test_td3_cfg_layout_is_shared_by_the_binding_and_the_restatement():
     oa, oc = C.c_int(), C.c_int()
     c_oracle.lib().le_oracle_td3_params(C.c_int(6), C.c_int(3), C.c_int(20), C.c_int(1), C.byref(oa), C.byref(oc))
     assert (pa.value, pc.value) == (oa.value, oc.value) == (6 * 20 + 20 + 20 * 3 + 3, 9 * 20 + 20 + 20 + 1)
+
+
+def test_td3_entry_rejects_bad_arguments_without_gpu():
+    lib = _abi.load_library()
+    t = _abi.Td3Cfg()
+    assert lib.le_td3_run_host(C.byref(t), None, 0, None, None, None, None, None, 1, None, 1, None, None, None, None, None, 0, 0) == -1
+    assert b"bad arguments" in lib.le_last_error()
+    import numpy as np
+    t.base.sd, t.base.ad, t.base.real_env, t.base.env_kind, t.base.rn_type = 4, 2, 0, 1, 2      # reward-network training env
+    t.base.env_hidden, t.base.q_hidden, t.base.q_layers, t.base.batch_size = 8, 8, 1, 4
+    t.base.train_episodes, t.base.test_episodes, t.base.max_steps, t.base.rb_size = 1, 1, 10, 100
+    t.policy_delay, t.gumbel_temp = 1, 1.0
+    keys = np.zeros((1, 2), np.uint32)
+    buf = np.zeros(4096, np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.le_td3_run_host(C.byref(t), p(buf), 1, None, p(keys), p(buf), p(buf), p(buf), 1, None, 1, p(buf), p(buf), p(buf), p(buf), None, 0, 0)
+    assert rc == -3 and b"reward-network" in lib.le_last_error()
