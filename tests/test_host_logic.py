@@ -221,6 +221,10 @@ def test_gtn_master_unknown_options_raise_like_the_reference(monkeypatch, tmp_pa
     m.score_list, m.score_orig_list = [1.0, 2.0, 3.0, 4.0], [1.0] * 4
     with pytest.raises(ValueError, match="Unknown rank transform type"):
         m.score_transform()
+    cfg = _small_gtn_config()
+    cfg["agents"]["gtn"]["agent_name"] = "TD3_discrete_vary"
+    with pytest.raises(NotImplementedError, match="population evaluator covers DDQN and DuelingDDQN"):
+        gtn.GTN_Master(cfg, evaluator_cls=OracleEvaluator, verbose=False)
 
 
 @pytest.mark.parametrize("mode", ["replicated", "allreduce"])
