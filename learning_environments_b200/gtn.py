@@ -134,10 +134,6 @@ class GTN_Master(GTN_Base):
             dist.broadcast(t, 0)
             self.seed = int(t.item())
         inner = self.agent_name.lower()
-        if inner not in ("ddqn", "duelingddqn"):
-            # the reference accepts any select_agent name here (agents/GTN_worker.py:190); the population evaluator is built for
-            # the DDQN / DuelingDDQN inner loops (TD3_discrete_vary lanes exist for evaluation: agents.TD3_discrete_vary)
-            raise NotImplementedError("GTN inner-loop agent %r: the population evaluator covers DDQN and DuelingDDQN" % self.agent_name)
         gamma = config["agents"][inner]["gamma"]
         self.lane_cfg = le_config.lane_cfg(config, inner, env_kind, use_test_env=True, final_test=True, step_budget=step_budget,
                                            gamma=gamma)

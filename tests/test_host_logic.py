@@ -223,7 +223,7 @@ def test_gtn_master_unknown_options_raise_like_the_reference(monkeypatch, tmp_pa
         m.score_transform()
     cfg = _small_gtn_config()
     cfg["agents"]["gtn"]["agent_name"] = "TD3_discrete_vary"
-    with pytest.raises(NotImplementedError, match="population evaluator covers DDQN and DuelingDDQN"):
+    with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
         gtn.GTN_Master(cfg, evaluator_cls=OracleEvaluator, verbose=False)
 
 
