@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — SE env-steps/s of the NES inner loop (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole_se|acrobot_se|cartpole_rn]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--extras all|none]
+                    [--scaling weak|strong] [--population P]
 
 One "step" = one NES generation's population evaluation over one batch of synthetic input: every member's SE is
 perturbed from the Philox stream (theta, theta+eps, theta-eps) and every resulting lane runs a complete, bounded
@@ -12,7 +13,12 @@ collective) and the generation ends with the all-gather of fitness scores + the 
 value  = training env-steps of all lanes of all ranks / device time (CUDA events, max over ranks), inputs resident in HBM
 e2e    = the same through PopulationEvaluator.evaluate() with HOST theta: H2D of theta/keys and D2H of lane results inside
 roofline.achieved = F_step (SURVEY.md §8d algorithmic flop per inner-loop step) x steps / fused-kernel time
-cpu_baseline      = oracle/le_oracle.c (C restatement of the reference's loop, kind "port") on the host cores
+with_update       = the same generation timed on the device INCLUDING the score all-gather (NCCL) + score transform + NES update
+workloads         = (default run, headline workload) every other named workload timed for 2-3 steps in the same process:
+                    acrobot_se, cartpole_rn, both DuelingDDQN workloads, sweep_h1024, vary_hp, the full-size-ring regime
+strong_scaling    = (default run) a FIXED population of 8 x 1184 members split over the ranks (scaling: strong)
+cpu_baseline      = the UNMODIFIED reference (oracle/_ref/pyref, staged by oracle/make_ref.py; kind "reference") on all host
+                    cores, one single-thread worker process per core; the C restatement (kind "port") is kept as a 2nd figure
 """
 import argparse
 import json
@@ -42,7 +48,12 @@ WORKLOADS = {
     # BASELINE config 4 (vary_hp evaluation): 4096 DDQN agents per GPU with per-lane lr / batch_size / hidden_size / hidden_layer
     # on ONE fixed CartPole SE, init_episodes=10, plateau early-out; train_episodes bounded (the evaluator's cap is 1000)
     "vary_hp": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=4096, train_episodes=30),
+    # the yaml's replay regime: rb_size 100 000 and a step budget large enough that the rings of all resident slots total > 4 GB
+    # (50 200 rows x 48 B x 1776 slots): the random 48-byte gathers come from HBM, not from the 126 MB L2
+    "cartpole_se_fullring": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=500, step_budget=50000),
 }
+EXTRA_WORKLOADS = ["acrobot_se", "cartpole_rn", "cartpole_se_dueling", "acrobot_se_dueling", "sweep_h1024", "cartpole_se_fullring", "vary_hp"]
+STRONG_POPULATION = 8 * 1184
 
 
 def build_lane_cfg(workload):
@@ -60,6 +71,8 @@ def build_lane_cfg(workload):
     if "grad_evals" in w:
         d["agents"]["gtn"]["num_grad_evals"] = w["grad_evals"]
     cfg = config.lane_cfg(d, name, ENV_SE if w["kind"] == "se" else ENV_RN, use_test_env=True, final_test=True)
+    if "step_budget" in w:
+        cfg.step_budget = w["step_budget"]
     return d, cfg
 
 
@@ -144,7 +157,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_baseline(cfg, theta, target_seconds, n_threads):
+def cpu_port_baseline(cfg, theta, target_seconds, n_threads):
     """Times the C restatement (oracle/) on a bounded sample of the same workload: `n` lanes on n_threads threads."""
     from oracle import c_oracle, philox
     c_oracle.build()
@@ -161,34 +174,107 @@ def cpu_baseline(cfg, theta, target_seconds, n_threads):
     return steps / dt, dict(lanes=n, steps=steps, seconds=dt, single_lane_seconds=t1, single_lane_steps=int(r1["train_steps"][0]))
 
 
+def reference_spec(workload):
+    """What oracle/ref_bench.py needs to run the UNMODIFIED reference on the lane configuration of `workload`."""
+    w = WORKLOADS[workload]
+    yaml_name = {"cartpole_syn_env": "default_config_cartpole_syn_env.yaml", "acrobot_syn_env": "default_config_acrobot_syn_env.yaml",
+                 "cartpole_reward_env": "default_config_cartpole_reward_env.yaml"}[w["cfg"]]
+    over = {"train_episodes": w["train_episodes"]}
+    if "init_episodes" in w:
+        over["init_episodes"] = w["init_episodes"]
+    env_over = {"hidden_size": w["env_hidden"]} if "env_hidden" in w else {}
+    return dict(yaml=yaml_name, agent=w.get("agent", "ddqn"), kind=w["kind"], agent_overrides=over, env_overrides=env_over)
+
+
+def cpu_reference_baseline(workload, cfg, theta, target_seconds, cores):
+    """The reference's own torch CPU path (unmodified, oracle/_ref/pyref or /root/reference) on `cores` single-thread worker
+    processes: one calc_score (fresh agent, train on the SE/RN with per-episode test(), final test()) per task.
+    Returns (env-steps/s aggregate, info) or None when the reference tree is not staged."""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        return None
+    from oracle import ref_bench
+    spec = reference_spec(workload)
+    n_tasks = max(cores, 16 * 3)                    # at least one NES generation of population 16 (3 calc_scores per member)
+    r = ref_bench.run(spec, theta, n_tasks, n_workers=cores, budget_s=target_seconds)
+    ts = np.array(r["task_seconds"])
+    value = r["steps"] / r["seconds"]
+    # one generation of the yaml's population (16 members x 3 calc_scores) on this machine, one worker per core:
+    # ceil(48 / workers) waves of the mean task time
+    gen_s = float(np.ceil(48.0 / r["workers"]) * ts.mean())
+    return value, dict(tasks=r["tasks"], steps=r["steps"], seconds=r["seconds"], workers=r["workers"], task_seconds_mean=float(ts.mean()),
+                       steps_per_s_per_core=value / r["workers"], nes_generations_per_hour_pop16=3600.0 / gen_s)
+
+
+def cpu_baseline_block(workload, cfg, target_seconds):
+    """cpu_baseline object of the JSON line: the unmodified reference when staged (kind "reference"), else the C port."""
+    cores = os.cpu_count() or 1
+    theta = synthetic_theta(cfg)
+    ref = cpu_reference_baseline(workload, cfg, theta, target_seconds, cores)
+    pv, pinfo = cpu_port_baseline(cfg, theta, target_seconds=min(target_seconds, 8.0), n_threads=cores)
+    port = {"value": pv, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d lanes, %d steps in %.1f s on %d pthreads (C restatement oracle/le_oracle.c)" % (pinfo["lanes"], pinfo["steps"], pinfo["seconds"], cores)}
+    if ref is None:
+        return port, None
+    v, info = ref
+    blk = {"value": v, "unit": "env-steps/s", "cores": info["workers"], "kind": "reference",
+           "sample": "%d calc_scores (fresh %s agent: train on the synthetic env with per-episode test(), final test()) of the UNMODIFIED "
+                     "reference, %d env steps in %.1f s on %d single-thread worker processes (torch %s CPU)" % (
+                         info["tasks"], reference_spec(workload)["agent"], info["steps"], info["seconds"], info["workers"], _torch_version()),
+           "steps_per_s_per_core": info["steps_per_s_per_core"], "nes_generations_per_hour_pop16": info["nes_generations_per_hour_pop16"],
+           "port": port}
+    return blk, info
+
+
+def _torch_version():
+    import torch
+    return torch.__version__
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (C restatement, all host threads)."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     d, cfg = build_lane_cfg(args.workload)
-    theta = synthetic_theta(cfg)
     cores = os.cpu_count() or 1
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        v, info = cpu_baseline(cfg, theta, target_seconds=3.0, n_threads=cores)
+    theta = synthetic_theta(cfg)
+    total = max(args.steps + args.warmup, 1)
+    per_step_s = max(6.0, min(40.0, 150.0 / total))      # the whole --steps K --warmup W run ends within a few minutes
+    tot_steps = tot_s = 0.0
+    infos = []
+    kind = "reference"
+    for i in range(total):
+        ref = cpu_reference_baseline(args.workload, cfg, theta, per_step_s, cores)
+        if ref is None:
+            kind = "port"
+            v, info = cpu_port_baseline(cfg, theta, target_seconds=3.0, n_threads=cores)
+            info = dict(info, tasks=info["lanes"], workers=cores, nes_generations_per_hour_pop16=None, steps_per_s_per_core=v / cores)
+        else:
+            v, info = ref
         if i >= args.warmup:
-            vals.append((v, info))
-    tot_steps = sum(i["steps"] for _, i in vals)
-    tot_s = sum(i["seconds"] for _, i in vals)
+            tot_steps += info["steps"]
+            tot_s += info["seconds"]
+            infos.append(info)
     value = tot_steps / tot_s
+    gph = [i["nes_generations_per_hour_pop16"] for i in infos if i.get("nes_generations_per_hour_pop16")]
+    sample = ("%d calc_scores per step of the same lane config on %d single-thread worker processes, UNMODIFIED reference (oracle/_ref/pyref)"
+              % (infos[-1]["tasks"], infos[-1]["workers"])) if kind == "reference" else \
+             ("%d lanes/step of the same lane config, C restatement oracle/le_oracle.c, %d pthreads" % (infos[-1]["tasks"], cores))
     line = {
         "impl": "reference", "metric": "se_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, cfg, 0, None),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d lanes/step of the same lane config (bounded calc_score), C restatement oracle/le_oracle.c, "
-                                   "%d pthreads" % (info["lanes"], cores)},
+        "nes_generations_per_hour": float(np.mean(gph)) if gph else None, "nes_population": 16,
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": infos[-1]["workers"], "kind": kind, "sample": sample,
+                         "steps_per_s_per_core": value / infos[-1]["workers"]},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if kind == "reference":
+        pv, pinfo = cpu_port_baseline(cfg, theta, target_seconds=3.0, n_threads=cores)
+        line["cpu_baseline"]["port"] = {"value": pv, "unit": "env-steps/s", "cores": cores, "kind": "port"}
     print(json.dumps(line))
     return 0
 
@@ -202,66 +288,94 @@ def workload_config(name, cfg, members_per_gpu, plan):
                          cfg.test_episodes),
          "members_per_gpu": members_per_gpu, "lanes_per_member": 1 + 2 * w.get("grad_evals", 1), "env_hidden": cfg.env_hidden,
          "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+    if cfg.step_budget:
+        c["step_budget_per_lane"] = int(cfg.step_budget)
     if plan:
-        c.update({"resident_warp_slots": plan["slots"], "replay_ring_rows": plan["ring_cap"], "units_per_thread": plan["units"]})
+        c.update({"resident_warp_slots": plan["slots"], "replay_ring_rows": plan["ring_cap"], "units_per_thread": plan["units"],
+                  "replay_rings_bytes": int(plan["slots"]) * int(plan["ring_cap"]) * (2 * cfg.sd + 4) * 4})
     return c
 
 
-def run_vary_hp_workload(args):
-    """--workload vary_hp: BASELINE config 4.  One step = every agent of this rank trained on the SE (virtual-env plateau rule)
-    and tested on the real env: one launch of the register kernel (hidden_layer <= 1, hidden_size <= 128) and one of the
-    general kernel (the rest), per-lane le_lane_cfg."""
+class Dist(object):
+    """torch.distributed plumbing of one bench process (one rank per GPU)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py --impl ours needs a CUDA device: the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_sum(self, values):
+        """(max over ranks, sum over ranks) of a list of floats."""
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return t.tolist(), t.tolist()
+        a, b = t.clone(), t.clone()
+        self.dist.all_reduce(a, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM)
+        return a.tolist(), b.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure_vary_hp(D, steps, warmup, members_per_gpu=0, ffma_peak=None):
+    """BASELINE config 4.  One step = every agent of this rank trained on the SE (virtual-env plateau rule) and tested on
+    the real env: one launch per kernel family (register kernel sets by hidden width, general kernel for the rest), per-lane
+    le_lane_cfg; the lane queue of every launch is ordered longest-first."""
     import torch
-    import torch.distributed as dist
     from learning_environments_b200 import default_configs, ops, vary_hp
     from learning_environments_b200.rng import lane_keys
-    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py --impl ours needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    dev, rank, world = D.dev, D.rank, D.world
     w = WORKLOADS["vary_hp"]
     d = default_configs.get(w["cfg"])
-    n = args.members_per_gpu or w["members_per_gpu"]
+    n = members_per_gpu or w["members_per_gpu"]
     over = dict(vary_hp.OVERRIDES, train_episodes=w["train_episodes"])
     cfgs = vary_hp.sample_agent_cfgs(d, n, np.random.RandomState(1000 + rank), over, True, None)
     theta_host = synthetic_theta(cfgs[0])
     theta_dev = torch.from_numpy(theta_host).to(dev).reshape(1, -1)
     groups = []
-    for resident in (True, False):
-        idx = np.array([i for i, c in enumerate(cfgs) if c.q_is_register_resident() == resident], int)
-        if len(idx):
-            sub = [cfgs[i] for i in idx]
-            cfg0 = vary_hp._max_cfg(sub)
-            groups.append(dict(idx=idx, sub=sub, cfg0=cfg0, bufs=ops.InnerLoopBuffers(cfg0, len(idx), 1, dev, n_cfg=len(idx))))
-    total = args.warmup + args.steps
+    for idx in vary_hp.launch_groups(cfgs):
+        sub = [cfgs[i] for i in idx]
+        cfg0 = vary_hp._max_cfg(sub)
+        groups.append(dict(idx=idx, idx_dev=torch.from_numpy(idx).to(dev), sub=sub, cfg0=cfg0,
+                           bufs=ops.InnerLoopBuffers(cfg0, len(idx), 1, dev, n_cfg=len(idx))))
+    total = warmup + steps
     keys = [torch.from_numpy(lane_keys(4321, g, rank * n + np.arange(n), np.zeros(n, int), np.zeros(n, int)).view(np.int32).copy()).to(dev)
             for g in range(total)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ffma_peak = ops.bench_ffma()
+    ffma_peak = ffma_peak or ops.bench_ffma()
 
     def step(g):
         for gr in groups:
-            ops.inner_loop_run(gr["bufs"], gr["sub"], theta_dev, None, keys[g][torch.from_numpy(gr["idx"]).to(dev)].contiguous(), cfg0=gr["cfg0"])
+            ops.inner_loop_run(gr["bufs"], gr["sub"], theta_dev, None, keys[g][gr["idx_dev"]].contiguous(), cfg0=gr["cfg0"])
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-    for g in range(args.warmup):
+    for g in range(warmup):
         step(g)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    D.barrier()
+    sampler = ClockSampler(D.local_rank)
     sampler.start()
     dev_ms, steps_done, flop = 0.0, 0, 0.0
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
+    for k in range(steps):
+        D.flush.fill_(k & 0xFF)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step(args.warmup + k)
+        step(warmup + k)
         e1.record()
         torch.cuda.synchronize()
         dev_ms += e0.elapsed_time(e1)
@@ -271,53 +385,197 @@ def run_vary_hp_workload(args):
             for c, st, li in zip(gr["sub"], res["train_steps"], res["learn_iters"]):
                 a, b = f_parts(c)
                 flop += float(st) * a + float(li) * b
-    barrier()
+    D.barrier()
     clocks = sampler.stop()
-    t = torch.tensor([dev_ms, float(steps_done), flop], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax, tsum = t.clone(), t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, steps_all, flop_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
-    else:
-        steps_all, flop_all = float(steps_done), flop
-    # end to end through the public API: sampling, H2D of theta / keys / per-lane cfgs, both launches, D2H of the results
-    barrier()
+    mx, sm = D.max_sum([dev_ms, float(steps_done), flop])
+    dev_ms, steps_all, flop_all = mx[0], sm[1], sm[2]
+    # end to end through the public API: sampling, H2D of theta / keys / per-lane cfgs, all launches, D2H of the results
+    D.barrier()
     t0 = time.perf_counter()
     e2e_steps = 0
-    for k in range(args.steps):
+    for k in range(steps):
         _, st, _, _ = vary_hp.evaluate_agents(d, theta_host.reshape(1, -1), n, seed=1000 + rank, overrides=over, device=dev, shard=False)
         e2e_steps += sum(st[0])
-    barrier()
+    D.barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s, float(e2e_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        a, b = te.clone(), te.clone()
-        dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_steps = float(a[0]), float(b[1])
-    if rank == 0:
-        achieved = flop_all / world / (dev_ms * 1e-3) / 1e12
-        n_gen = sum(len(g["idx"]) for g in groups if not g["cfg0"].q_is_register_resident())
-        line = {
-            "metric": "se_env_steps_per_s", "value": steps_all / (dev_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "vary_hp: %d DDQN_vary agents per GPU on one CartPole SE (lr, batch_size in [66,597], hidden_size in "
-                                   "[19,171], hidden_layer in {1,2} per lane), init_episodes=10, <=%d train episodes, plateau early-out, "
-                                   "final test() of 10 real-env episodes" % (n, w["train_episodes"]),
-                       "agents_per_gpu": n, "general_kernel_lanes": n_gen, "l2": "256 MiB buffer written between timed steps (L2 flush)"},
-            "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s",
-                    "h2d_bytes_per_step": int(theta_host.nbytes + n * 8 + n * 200), "d2h_bytes_per_step": int(n * (40 + 10 * 8))},
-            "gpu_launches": (1 + len(groups)) * args.steps, "clocks": clocks,
-            "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / ffma_peak if ffma_peak else None, "traffic": None,
-                         "peak_source": "le_bench_ffma microbenchmark in this run"},
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    mx, sm = D.max_sum([e2e_s, float(e2e_steps)])
+    e2e_s, e2e_steps = mx[0], sm[1]
+    achieved = flop_all / world / (dev_ms * 1e-3) / 1e12
+    n_gen = sum(len(g["idx"]) for g in groups if not g["cfg0"].q_is_register_resident())
+    return {
+        "metric": "se_env_steps_per_s", "value": steps_all / (dev_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "vary_hp: %d DDQN_vary agents per GPU on one CartPole SE (lr, batch_size in [66,597], hidden_size in "
+                               "[19,171], hidden_layer in {1,2} per lane), init_episodes=10, <=%d train episodes, plateau early-out, "
+                               "final test() of 10 real-env episodes" % (n, w["train_episodes"]),
+                   "agents_per_gpu": n, "general_kernel_lanes": n_gen, "launches_per_step": len(groups),
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)"},
+        "seconds_per_evaluation": dev_ms * 1e-3 / max(steps, 1),
+        "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s",
+                "h2d_bytes_per_step": int(theta_host.nbytes + n * 8 + n * 200), "d2h_bytes_per_step": int(n * (40 + 10 * 8))},
+        "gpu_launches": (1 + len(groups)) * steps, "clocks": clocks,
+        "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
+                     "frac": achieved / ffma_peak if ffma_peak else None, "traffic": None,
+                     "peak_source": "le_bench_ffma microbenchmark in this run"},
+    }
+
+
+def measure_nes(D, workload, steps, warmup, members_per_gpu=0, population=0, lane_override=(), ffma_peak=None, with_e2e=True):
+    """One NES-generation workload on this process group: device-timed `value`, the generation including the score exchange
+    and the NES update (`with_update`), and (with_e2e) the end-to-end figure through the host API.  Returns the JSON fields."""
+    import torch
+    from learning_environments_b200 import ops
+    from learning_environments_b200.engine import PopulationEvaluator
+    from learning_environments_b200.nes import score_transform
+    from learning_environments_b200.rng import lane_keys
+    dist, dev, world, rank = D.dist, D.dev, D.world, D.rank
+    d, cfg = build_lane_cfg(workload)
+    for ov in lane_override:
+        k, v = ov.split("=")
+        setattr(cfg, k, type(getattr(cfg, k))(float(v)))
+    gtn = d["agents"]["gtn"]
+    if population:                                   # strong scaling: a fixed population split over the ranks
+        mpg = (population + world - 1) // world
+        pop = mpg * world
+    else:
+        mpg = members_per_gpu or WORKLOADS[workload]["members_per_gpu"]
+        pop = mpg * world
+    ev = PopulationEvaluator(cfg, pop, member_lo=rank * mpg, member_hi=(rank + 1) * mpg, num_grad_evals=gtn["num_grad_evals"],
+                             seed=1234, noise_std=gtn["noise_std"], device=dev)
+    plan = ops.inner_loop_plan(cfg, ev.n_lanes, ev.n_env)
+    theta_host = torch.from_numpy(synthetic_theta(cfg)).pin_memory()
+    theta_dev = theta_host.to(dev)
+    theta_work = theta_dev.clone()
+    scores_all = torch.zeros((world, mpg, 2), dtype=torch.float64, device=dev)
+    scores_host = torch.zeros((world, mpg, 2), dtype=torch.float64).pin_memory()
+    coef_host = torch.zeros(pop, dtype=torch.float32).pin_memory()
+    coef_dev = torch.zeros(pop, dtype=torch.float32, device=dev)
+    sign_dev = torch.ones(pop, dtype=torch.float32, device=dev)
+    ffma_peak = ffma_peak or ops.bench_ffma()
+    total = warmup + steps
+    # lane keys are precomputed (host-side key derivation is not the timed work of the device-resident figures)
+    key_cache = {}
+
+    def keys_for(gen):
+        if gen not in key_cache:
+            k = lane_keys(ev.seed, gen, ev.lane_member, ev.lane_variant, ev.lane_eval)
+            key_cache[gen] = torch.from_numpy(k.view(np.int32).copy()).to(dev)
+        return key_cache[gen]
+    for g in range(3 * total + 3):
+        keys_for(g)
+
+    def launch_resident(gen):
+        ev._theta_dev.copy_(theta_dev)
+        ev._keys_dev.copy_(keys_for(gen))
+        thetas = ops.nes_perturb(ev._theta_dev, ev.pop, ev.member_lo, ev.n_members, ev.seed, gen, ev.noise_std)
+        ops.inner_loop_run(ev.bufs, cfg, thetas, ev.env_index, ev._keys_dev)
+        ev._thetas = thetas
+
+    def exchange_and_update(out, gen):
+        """score all-gather over the ranks (NCCL), identical score transform on every rank, NES update of theta."""
+        orig, add, sub = ev.member_scores(out)
+        local = torch.from_numpy(np.stack([np.maximum(add, sub), orig], 1)).to(dev, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(scores_all.view(-1), local.view(-1))
+            scores_host.copy_(scores_all, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            sc = scores_host.numpy().reshape(pop, 2)
+        else:
+            sc = np.stack([np.maximum(add, sub), orig], 1)
+        wgt = score_transform(sc[:, 0], sc[:, 1], gtn["score_transform_type"])
+        coef_host.copy_(torch.from_numpy((gtn["step_size"] * wgt).astype(np.float32)))
+        coef_dev.copy_(coef_host, non_blocking=True)
+        theta_work.copy_(theta_dev)
+        # every rank regenerates all eps_i and applies them in member order: bit-identical theta on all ranks
+        ops.nes_update(theta_work, pop, ev.seed, gen, ev.noise_std, gtn["weight_decay"], coef_dev, sign_dev)
+
+    def timed(fn, first_gen):
+        for g in range(warmup):
+            fn(first_gen + g)
+        D.barrier()
+        sampler = ClockSampler(D.local_rank)
+        sampler.start()
+        ms, st, li = 0.0, 0, 0
+        for k in range(steps):
+            D.flush.fill_(k & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(first_gen + warmup + k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+            res = ev.bufs.results()
+            st += int(res["train_steps"].sum())
+            li += int(res["learn_iters"].sum())
+        D.barrier()
+        clocks = sampler.stop()
+        mx, sm = D.max_sum([ms, float(st), float(li)])
+        return mx[0], sm[1], sm[2], clocks
+
+    # ---------------- device-resident: population evaluation only (value) ----------------
+    dev_ms, steps_all, learn_all, clocks = timed(launch_resident, 0)
+    value = steps_all / (dev_ms * 1e-3)
+
+    # ---------------- device-resident generation INCLUDING the collective and the NES update ----------------
+    def generation_with_update(gen):
+        launch_resident(gen)
+        exchange_and_update(ev.collect(), gen)
+    upd_ms, upd_steps, _, _ = timed(generation_with_update, total)
+    f_env_q, f_td = f_parts(cfg)
+    # per-GPU TFLOP/s of algorithmic work: every env step costs F_env + F_q, every TD update 5*B*F_q (steps of the
+    # init_episodes do not learn); the fused kernel is >= 95% of the timed region (profiles/)
+    achieved = (steps_all * f_env_q + learn_all * f_td) / world / (dev_ms * 1e-3) / 1e12
+    res = {
+        "metric": "se_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong" if population else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(workload, cfg, mpg, plan), **({"overrides": list(lane_override)} if lane_override else {})),
+        "nes_population": pop,
+        "with_update": {"value": upd_steps / (upd_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": upd_ms / max(steps, 1),
+                        "what": "device-timed generation incl. D2H of lane results, score all-gather (NCCL), score transform, NES update kernel"},
+        "gpu_launches": 3 * steps,
+        "clocks": clocks,
+        "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
+                     "frac": achieved / ffma_peak if ffma_peak else None,
+                     "traffic": _ncu_traffic(workload, steps_all / world / max(steps, 1)),
+                     "flop_per_env_step": f_step(cfg), "td_updates_per_env_step": learn_all / max(steps_all, 1.0),
+                     "peak_source": "le_bench_ffma microbenchmark in this run (FP32 FFMA; MEASURED_PEAKS.json has no FP32 figure)",
+                     "hbm": {"algorithmic_bytes_per_env_step": (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4,
+                             "achieved_gbs": value / world * (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4 / 1e9,
+                             "peak_gbs": _measured_hbm()}},
+    }
+    if with_e2e:
+        # ---------------- end-to-end through the host API (e2e): HOST theta in, lane results out, every generation -------------
+        base = 2 * total
+        for g in range(warmup):
+            ev.evaluate(theta_host, base + g)
+        D.barrier()
+        t0 = time.perf_counter()
+        e2e_steps = 0
+        for k in range(steps):
+            gen = base + warmup + k
+            out = ev.evaluate(theta_host, gen)          # H2D theta/keys, kernels, D2H lane results
+            e2e_steps += int(out["train_steps"].sum())
+            exchange_and_update(out, gen)
+        D.barrier()
+        e2e_s = time.perf_counter() - t0
+        mx, sm = D.max_sum([e2e_s, float(e2e_steps)])
+        res["e2e"] = {"value": sm[1] / mx[0], "unit": "env-steps/s", "h2d_bytes_per_step": ev.h2d_bytes, "d2h_bytes_per_step": ev.d2h_bytes}
+        res["nes_generations_per_hour"] = 3600.0 / (mx[0] / max(steps, 1))
+    del ev
+    torch.cuda.empty_cache()
+    return res, cfg
+
+
+def compact(r):
+    """Sub-workload entry of the headline line's `workloads` object."""
+    out = {"value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "steps": r["steps"], "warmup": r["warmup"],
+           "frac": r["roofline"]["frac"], "achieved_tflops": r["roofline"]["achieved"], "clocks": r["clocks"], "config": r["config"]}
+    for k in ("with_update", "e2e", "seconds_per_evaluation", "nes_population"):
+        if k in r:
+            out[k] = r[k]
+    return out
 
 
 def main():
@@ -328,188 +586,60 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cartpole_se", choices=sorted(WORKLOADS))
     ap.add_argument("--members-per-gpu", type=int, default=0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --population members split over the ranks")
+    ap.add_argument("--population", type=int, default=0, help="total NES population for --scaling strong (default 8 x 1184)")
+    ap.add_argument("--extras", default="auto", choices=["auto", "all", "none"],
+                    help="auto: the default headline run also times every other workload + the strong-scaling point")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lane-override", action="append", default=[], metavar="FIELD=VALUE",
                     help="profiling aid: override an le_lane_cfg field (e.g. max_steps=100); recorded in config.overrides")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    if args.workload == "vary_hp":
-        return run_vary_hp_workload(args)
-
-    import torch
-    import torch.distributed as dist
+    D = Dist()
     from learning_environments_b200 import ops
-    from learning_environments_b200.engine import PopulationEvaluator
-    from learning_environments_b200.nes import score_transform
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py --impl ours needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    d, cfg = build_lane_cfg(args.workload)
-    for ov in args.lane_override:
-        k, v = ov.split("=")
-        setattr(cfg, k, type(getattr(cfg, k))(float(v)))
-    gtn = d["agents"]["gtn"]
-    mpg = args.members_per_gpu or WORKLOADS[args.workload]["members_per_gpu"]
-    pop = mpg * world
-    ev = PopulationEvaluator(cfg, pop, member_lo=rank * mpg, member_hi=(rank + 1) * mpg, num_grad_evals=gtn["num_grad_evals"],
-                             seed=1234, noise_std=gtn["noise_std"], device=dev)
-    plan = ops.inner_loop_plan(cfg, ev.n_lanes, ev.n_env)
-    theta_host = torch.from_numpy(synthetic_theta(cfg)).pin_memory()
-    theta_dev = theta_host.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    scores_all = torch.zeros((world, mpg, 2), dtype=torch.float64, device=dev)
-    coef_dev = torch.zeros(pop, dtype=torch.float32, device=dev)
-    sign_dev = torch.ones(pop, dtype=torch.float32, device=dev)
     ffma_peak = ops.bench_ffma()
-
-    def generation(gen, host_path):
-        """One NES generation. host_path: theta from pinned HOST memory + results read back (e2e)."""
-        if host_path:
-            out = ev.evaluate(theta_host, gen)
-        else:
-            ev._theta_dev.copy_(theta_dev)
-            ev._keys_dev.copy_(ev._keys_for(gen))
-            thetas = ops.nes_perturb(ev._theta_dev, ev.pop, ev.member_lo, ev.n_members, ev.seed, gen, ev.noise_std)
-            ops.inner_loop_run(ev.bufs, cfg, thetas, ev.env_index, ev._keys_dev)
-            ev._thetas = thetas
-            out = None
-        return out
-
-    # lane keys for the device-resident path are precomputed (host-side key derivation is not the timed work)
-    from learning_environments_b200.rng import lane_keys
-    key_cache = {}
-
-    def keys_for(gen):
-        if gen not in key_cache:
-            k = lane_keys(ev.seed, gen, ev.lane_member, ev.lane_variant, ev.lane_eval)
-            key_cache[gen] = torch.from_numpy(k.view(np.int32).copy()).to(dev)
-        return key_cache[gen]
-    ev._keys_for = keys_for
-    total = args.warmup + args.steps
-    for g in range(2 * total + 2):
-        keys_for(g)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---------------- device-resident timing (value) ----------------
-    for g in range(args.warmup):
-        generation(g, False)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev_pairs = []
-    steps_done = 0
-    learn_done = 0
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        generation(args.warmup + k, False)
-        e1.record()
-        ev_pairs.append((e0, e1))
-        torch.cuda.synchronize()
-        res_k = ev.bufs.results()
-        steps_done += int(res_k["train_steps"].sum())
-        learn_done += int(res_k["learn_iters"].sum())
-    barrier()
-    clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev_pairs)
-    t = torch.tensor([dev_ms, float(steps_done), float(learn_done)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, steps_all, learn_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    plain = args.workload == "cartpole_se" and not args.lane_override and not args.members_per_gpu and args.scaling == "weak"
+    extras = args.extras == "all" or (args.extras == "auto" and plain and not args.no_cpu_baseline)
+    if args.workload == "vary_hp":
+        line = measure_vary_hp(D, args.steps, args.warmup, args.members_per_gpu, ffma_peak)
+        cfg = None
     else:
-        steps_all, learn_all = float(steps_done), float(learn_done)
-    value = steps_all / (dev_ms * 1e-3)
-
-    # ---------------- end-to-end timing through the host API (e2e) ----------------
-    base = total
-    for g in range(args.warmup):
-        generation(base + g, True)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = 0
-    for k in range(args.steps):
-        out = generation(base + args.warmup + k, True)          # H2D theta/keys, kernels, D2H lane results
-        e2e_steps += int(out["train_steps"].sum())
-        orig, add, sub = ev.member_scores(out)
-        local = torch.from_numpy(np.stack([np.maximum(add, sub), orig], 1)).to(dev)
-        if world > 1:
-            dist.all_gather_into_tensor(scores_all.view(-1), local.view(-1))   # per-generation all-gather of fitness scores
-            sc = scores_all.cpu().numpy().reshape(pop, 2)
-        else:
-            sc = local.cpu().numpy()
-        w = score_transform(sc[:, 0], sc[:, 1], gtn["score_transform_type"])
-        coef_dev.copy_(torch.from_numpy((gtn["step_size"] * w).astype(np.float32)))
-        # every rank regenerates all eps_i and applies them in member order: bit-identical theta on all ranks
-        ops.nes_update(theta_dev.clone(), pop, ev.seed, base + args.warmup + k, ev.noise_std, gtn["weight_decay"], coef_dev, sign_dev)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s, float(e2e_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_steps_all = float(a[0]), float(b[1])
-    else:
-        e2e_steps_all = float(e2e_steps)
-    e2e_value = e2e_steps_all / e2e_s
-
-    if rank == 0:
-        F = f_step(cfg)
-        f_env_q, f_td = f_parts(cfg)
-        # per-GPU TFLOP/s of algorithmic work: every env step costs F_env + F_q, every TD update 5*B*F_q (steps of the
-        # init_episodes do not learn); the fused kernel is >= 95% of the timed region (profiles/)
-        achieved = (steps_all * f_env_q + learn_all * f_td) / world / (dev_ms * 1e-3) / 1e12
-        line = {
-            "metric": "se_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args.workload, cfg, mpg, plan), **({"overrides": args.lane_override} if args.lane_override else {})),
-            "nes_generations_per_hour": 3600.0 / (e2e_s / max(args.steps, 1)), "nes_population": pop,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": ev.h2d_bytes, "d2h_bytes_per_step": ev.d2h_bytes},
-            "gpu_launches": 3 * args.steps,
-            "clocks": clocks,
-            "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / ffma_peak if ffma_peak else None,
-                         "traffic": _ncu_traffic(steps_all / world / max(args.steps, 1)),
-                         "flop_per_env_step": F, "td_updates_per_env_step": learn_all / max(steps_all, 1.0), "peak_source": "le_bench_ffma microbenchmark in this run (FP32 FFMA; "
-                                                                "MEASURED_PEAKS.json has no FP32 figure)",
-                         "hbm": {"algorithmic_bytes_per_env_step": (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4,
-                                 "achieved_gbs": value / world * (cfg.batch_size + 1) * (2 * cfg.sd + 3) * 4 / 1e9,
-                                 "peak_gbs": _measured_hbm()}},
-        }
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, info = cpu_baseline(cfg, synthetic_theta(cfg), target_seconds=12.0, n_threads=cores)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d lanes of the same lane config, %d steps in %.1f s on %d pthreads (C restatement "
-                                              "oracle/le_oracle.c; the reference's own torch path is ~0.8k steps/s/core, BASELINE.md)"
-                                              % (info["lanes"], info["steps"], info["seconds"], cores)}
+        pop = (args.population or STRONG_POPULATION) if args.scaling == "strong" else 0
+        line, cfg = measure_nes(D, args.workload, args.steps, args.warmup, args.members_per_gpu, pop, args.lane_override, ffma_peak)
+    if extras:
+        wl = {}
+        for name in EXTRA_WORKLOADS:
+            try:
+                if name == "vary_hp":
+                    wl[name] = compact(measure_vary_hp(D, 1, 1, 0, ffma_peak))
+                else:
+                    heavy = name == "cartpole_se_fullring"
+                    r, _ = measure_nes(D, name, 1 if heavy else 2, 1, 0, 0, (), ffma_peak, with_e2e=False)
+                    wl[name] = compact(r)
+            except Exception as e:   # a failing side workload must not lose the headline line
+                wl[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        line["workloads"] = wl
+        try:
+            r, _ = measure_nes(D, args.workload, 2, 1, 0, STRONG_POPULATION, (), ffma_peak, with_e2e=False)
+            line["strong_scaling"] = dict(compact(r), population=STRONG_POPULATION, scaling="strong",
+                                          note="fixed population split over the ranks: efficiency(N) = value(N) / (N * value(1))")
+        except Exception as e:
+            line["strong_scaling"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if D.rank == 0:
+        if not args.no_cpu_baseline and cfg is not None:
+            blk, _ = cpu_baseline_block(args.workload, cfg, target_seconds=20.0)
+            line["cpu_baseline"] = blk
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.barrier()
+    D.close()
     return 0
 
 
-def _ncu_traffic(env_steps_per_launch):
-    """DRAM bytes per launch of the fused kernel from the committed `ncu --set full` capture (profiles/), scaled to
-    this run's env steps per launch; None if no capture is committed."""
+def _ncu_traffic(workload, env_steps_per_launch):
+    """DRAM bytes per launch of the fused kernel from the committed `ncu` capture of THIS workload (profiles/r*_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one launch, divided by its env steps), scaled to this run's env steps
+    per launch; None if no capture of the workload is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
     if not files:
@@ -517,7 +647,8 @@ def _ncu_traffic(env_steps_per_launch):
     try:
         with open(files[-1]) as f:
             t = json.load(f)
-        return t["dram_bytes_per_env_step"] * env_steps_per_launch
+        t = t.get("workloads", {}).get(workload, t if workload == "cartpole_se" else None)
+        return t["dram_bytes_per_env_step"] * env_steps_per_launch if t else None
     except Exception:
         return None
 

@@ -164,6 +164,15 @@ int le_td_update(const le_lane_cfg* cfg, float* q_theta_dev, float* q_target_dev
                  float* adam_v_dev, int32_t* adam_t_dev, int n, const float* batch_rows_dev /*[n][B][2sd+3]*/,
                  float* loss_dev, void* stream);
 
+/* One dense-layer GEMM on the tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM) with the contract of the general
+ * kernel's dense layers: C[i*c_si + j*c_sj] (+)= sum_l A[i*a_si + l*a_sl] * B[l*b_sl + j*b_sj] (+ bias[j], activation
+ * act: 0 identity, 1 tanh, 2 leaky family with `slope`).  Covers nn.Linear forward (models/model_utils.py:22-36, X W^T),
+ * its input gradient (dZ W) and weight gradient (dZ^T X) as torch.autograd computes them for DDQN.learn /
+ * DuelingDDQN.learn (agents/DuelingDDQN.py:59-94).  Unit operator for the parity tests; the lane kernels call the same
+ * device routine (csrc/le_tc.cuh). */
+int le_tc_gemm(const float* A_dev, int a_si, int a_sl, const float* B_dev, int b_sl, int b_sj, float* C_dev, int c_si, int c_sj,
+               int I, int J, int L, const float* bias_dev, int act, float slope, int accumulate, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* the fused hot path                                                                               */
 

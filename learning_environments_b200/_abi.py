@@ -74,7 +74,18 @@ class LaneCfg(C.Structure):
 
     def q_is_register_resident(self):
         """True when the warp-per-lane register kernel set covers this Q-net (else the general CTA-per-lane kernel)."""
-        return self.q_kind == Q_DQN and self.q_layers <= 1 and self.q_hidden <= 128
+        return self.q_kind == Q_DQN and self.q_layers <= 1 and self.q_hidden <= self.max_register_hidden()
+
+    def max_register_hidden(self):
+        """Widest single-hidden-layer Critic_DQN of the compiled warp-per-lane kernel sets (32 hidden units per thread-unit U;
+        U in {2,4}, plus U = 6 for the CartPole shapes: DDQN_vary samples hidden_size in [19,171])."""
+        return 192 if (self.sd == 4 and self.ad == 2) else 128
+
+    def register_units(self):
+        """Hidden units per thread (U) of the kernel set that runs this lane, or 0 for the general kernel."""
+        if not self.q_is_register_resident():
+            return 0
+        return 2 if self.q_hidden <= 64 else (4 if self.q_hidden <= 128 else 6)
 
 
 class Td3Cfg(C.Structure):
@@ -123,7 +134,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "le_version", "le_last_error", "le_sizeof_lane_cfg", "le_device_info", "le_bench_ffma",
-    "le_se_forward", "le_rn_reward", "le_qnet_forward", "le_real_env_step", "le_td_update",
+    "le_se_forward", "le_rn_reward", "le_qnet_forward", "le_real_env_step", "le_td_update", "le_tc_gemm",
     "le_inner_loop_workspace_bytes", "le_inner_loop_plan", "le_inner_loop_run", "le_inner_loop_run_host",
     "le_nes_perturb", "le_nes_noise", "le_nes_update", "le_nes_partial_update",
     "le_td3_param_counts", "le_td3_run_host",

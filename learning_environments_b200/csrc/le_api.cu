@@ -67,7 +67,10 @@ static const InstanceOps* instance_for(const le_lane_cfg* c, int max_hidden) {
     return o;
 }
 
-static bool is_register_resident(const le_lane_cfg* c) { return c->q_kind == LE_Q_DQN && c->q_layers <= 1 && c->q_hidden <= 128; }
+// Critic_DQN with one hidden layer whose width fits a compiled warp-per-lane kernel set: 32*U hidden units, U in {2,4} and,
+// for the CartPole shapes, U = 6 (DDQN_vary samples hidden_size in [19,171], agents/DDQN_vary.py:26-59)
+static int max_register_hidden(const le_lane_cfg* c) { return (c->sd == 4 && c->ad == 2) ? 192 : 128; }
+static bool is_register_resident(const le_lane_cfg* c) { return c->q_kind == LE_Q_DQN && c->q_layers <= 1 && c->q_hidden <= max_register_hidden(c); }
 static int q_params_of(const le_lane_cfg* c) {
     return is_register_resident(c) ? c->q_hidden * (c->sd + c->ad + 1) + c->ad : general_q_params(c);
 }
@@ -152,32 +155,62 @@ __global__ void nes_noise_kernel(int P, int member_offset, int n_members, uint32
     }
 }
 
-// update_env (agents/GTN_master.py:267-298): one thread owns 4 parameters and walks the members IN ORDER, so the
-// fp32 accumulation order equals the reference's sequential loop for any grid / GPU count.
+// update_env (agents/GTN_master.py:267-298).  The reference accumulates theta += ss * w_i * eps_i SEQUENTIALLY in member order
+// in fp32, so the adds of one parameter form a serial chain; what is expensive is regenerating eps_i (Philox + fp64
+// Box-Muller: two log + two sincos per 4 normals).  A CTA owns kNesPT blocks of 4 parameters; its kNesMG "member groups"
+// (threads) generate the terms coef_i * eps_i of a TILE of kNesMG members in parallel into shared memory, then the kNesPT
+// threads of group 0 add the tile in member order: the fp32 accumulation order equals the reference's loop for any grid /
+// tile / GPU count (bit-identical theta on 1/2/4/8 ranks), while the normal generation runs kNesMG-wide.
+constexpr int kNesPT = 4, kNesMG = 256;
 template <bool FULL>
-__global__ void nes_update_kernel(float* __restrict__ theta, int P, int member_lo, int member_hi, uint32_t seed, uint32_t gen,
-                                  float noise_std, float one_minus_wd, const float* __restrict__ coef, const float* __restrict__ sign) {
+__global__ void __launch_bounds__(kNesPT * kNesMG)
+nes_update_kernel(float* __restrict__ theta, int P, int member_lo, int member_hi, uint32_t seed, uint32_t gen, float noise_std,
+                  float one_minus_wd, const float* __restrict__ coef, const float* __restrict__ sign) {
+    __shared__ float4 terms[2][kNesMG][kNesPT];
     const int nblk = (P + 3) / 4;
-    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x) {
-        float acc[4];
+    const int pt = threadIdx.x % kNesPT, g = threadIdx.x / kNesPT;
+    const int blk = blockIdx.x * kNesPT + pt;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (FULL && g == 0 && blk < nblk) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int p = blk * 4 + k;
             // l_orig.weight * (1 - weight_decay): python float (1 - wd) applied as an fp32 scalar
-            acc[k] = FULL ? (p < P ? __fmul_rn(theta[p], one_minus_wd) : 0.f) : 0.f;
+            acc[k] = p < P ? __fmul_rn(theta[p], one_minus_wd) : 0.f;
         }
-        for (int i = member_lo; i < member_hi; ++i) {
+    }
+    int buf = 0;
+    for (int i0 = member_lo; i0 < member_hi; i0 += kNesMG, buf ^= 1) {
+        const int i = i0 + g;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < member_hi && blk < nblk) {
             const float cf = coef[i];
-            if (cf == 0.f && !FULL) continue;
-            float z[4];
-            normals4((uint32_t)blk, (uint32_t)i, seed, gen, z);
-            const float sg = sign[i];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float e = __fmul_rn(__fmul_rn(z[k], noise_std), sg);  // eps (already carrying its sign)
-                acc[k] = __fadd_rn(acc[k], __fmul_rn(cf, e));               // l_orig.weight + ss*score_transform*l_eps.weight
+            if (cf != 0.f) {   // a zero coefficient adds an exact zero in the reference's loop
+                float z[4];
+                normals4((uint32_t)blk, (uint32_t)i, seed, gen, z);
+                const float sg = sign[i];
+                // eps (already carrying its sign), then ss * score_transform * eps
+                t.x = __fmul_rn(cf, __fmul_rn(__fmul_rn(z[0], noise_std), sg));
+                t.y = __fmul_rn(cf, __fmul_rn(__fmul_rn(z[1], noise_std), sg));
+                t.z = __fmul_rn(cf, __fmul_rn(__fmul_rn(z[2], noise_std), sg));
+                t.w = __fmul_rn(cf, __fmul_rn(__fmul_rn(z[3], noise_std), sg));
             }
         }
+        terms[buf][g][pt] = t;
+        __syncthreads();   // one barrier per tile: the other buffer is only rewritten after the NEXT barrier
+        if (g == 0) {
+            const int n = min(kNesMG, member_hi - i0);
+#pragma unroll 8
+            for (int m = 0; m < n; ++m) {
+                const float4 v = terms[buf][m][pt];
+                acc[0] = __fadd_rn(acc[0], v.x);   // l_orig.weight + ss*score_transform*l_eps.weight, member order
+                acc[1] = __fadd_rn(acc[1], v.y);
+                acc[2] = __fadd_rn(acc[2], v.z);
+                acc[3] = __fadd_rn(acc[3], v.w);
+            }
+        }
+    }
+    if (g == 0 && blk < nblk) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int p = blk * 4 + k;
@@ -696,8 +729,8 @@ int le_nes_update(float* theta_dev, int P, int pop, uint32_t seed, uint32_t gene
                   const float* coef_dev, const float* sign_dev, void* stream) {
     if (!theta_dev || !coef_dev || !sign_dev || P < 1 || pop < 1) { le_set_error("le_nes_update: bad arguments"); return LE_EINVAL; }
     const int nblk = (P + 3) / 4;
-    nes_update_kernel<true><<<(nblk + 63) / 64, 64, 0, (cudaStream_t)stream>>>(theta_dev, P, 0, pop, seed, generation, noise_std,
-                                                                            (float)(1.0 - weight_decay), coef_dev, sign_dev);
+    nes_update_kernel<true><<<(nblk + kNesPT - 1) / kNesPT, kNesPT * kNesMG, 0, (cudaStream_t)stream>>>(
+        theta_dev, P, 0, pop, seed, generation, noise_std, (float)(1.0 - weight_decay), coef_dev, sign_dev);
     LE_CUDA_CHECK(cudaGetLastError());
     return LE_OK;
 }
@@ -706,8 +739,8 @@ int le_nes_partial_update(float* delta_dev, int P, int member_lo, int member_hi,
                           const float* coef_dev, const float* sign_dev, void* stream) {
     if (!delta_dev || !coef_dev || !sign_dev || P < 1 || member_lo < 0 || member_hi < member_lo) { le_set_error("le_nes_partial_update: bad arguments"); return LE_EINVAL; }
     const int nblk = (P + 3) / 4;
-    nes_update_kernel<false><<<(nblk + 63) / 64, 64, 0, (cudaStream_t)stream>>>(delta_dev, P, member_lo, member_hi, seed, generation, noise_std,
-                                                                             1.f, coef_dev, sign_dev);
+    nes_update_kernel<false><<<(nblk + kNesPT - 1) / kNesPT, kNesPT * kNesMG, 0, (cudaStream_t)stream>>>(
+        delta_dev, P, member_lo, member_hi, seed, generation, noise_std, 1.f, coef_dev, sign_dev);
     LE_CUDA_CHECK(cudaGetLastError());
     return LE_OK;
 }

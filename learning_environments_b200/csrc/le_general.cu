@@ -6,8 +6,16 @@ namespace le {
 
 static int general_occupancy(int sd) {
     int nb = 0;
-    if (sd == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, general_loop_kernel<4, 2>, kGThreads, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, general_loop_kernel<6, 3>, kGThreads, 0);
+    // dynamic shared memory = the operand parts of the tcgen05 GEMM (le_tc.cuh); two CTAs per SM also bound the TMEM use
+    // (2 x 128 of the SM's 512 accumulator columns)
+    if (sd == 4) {
+        cudaFuncSetAttribute(general_loop_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, general_loop_kernel<4, 2>, kGThreads, tc::kSmemBytes);
+    } else {
+        cudaFuncSetAttribute(general_loop_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, general_loop_kernel<6, 3>, kGThreads, tc::kSmemBytes);
+    }
+    if (nb > 2) nb = 2;
     return nb < 1 ? 1 : nb;
 }
 
@@ -34,8 +42,11 @@ cudaError_t general_launch(const le_lane_cfg* c, const RunParams& rp, float* slo
     G.slots = slots;
     G.slot_stride = gp.slot_floats;
     G.bmax = gp.bmax;
-    if (c->sd == 4) general_loop_kernel<4, 2><<<gp.grid, kGThreads, 0, st>>>(G);
-    else general_loop_kernel<6, 3><<<gp.grid, kGThreads, 0, st>>>(G);
+    cudaError_t e = c->sd == 4 ? cudaFuncSetAttribute(general_loop_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)
+                               : cudaFuncSetAttribute(general_loop_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (c->sd == 4) general_loop_kernel<4, 2><<<gp.grid, kGThreads, tc::kSmemBytes, st>>>(G);
+    else general_loop_kernel<6, 3><<<gp.grid, kGThreads, tc::kSmemBytes, st>>>(G);
     return cudaGetLastError();
 }
 
@@ -47,8 +58,13 @@ int general_td_update(const le_lane_cfg* cfg, const le_lane_cfg* cfg_dev, float*
     const int64_t stride = gslot_floats(n, 0, 0, cfg->batch_size, offs);
     float* scratch = nullptr;
     LE_CUDA_CHECK(cudaMallocAsync((void**)&scratch, (size_t)stride * 4 * n_lanes, st));
-    if (cfg->sd == 4) general_td_update_kernel<4, 2><<<n_lanes, kGThreads, 0, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, cfg->batch_size, loss, scratch, stride);
-    else general_td_update_kernel<6, 3><<<n_lanes, kGThreads, 0, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, cfg->batch_size, loss, scratch, stride);
+    if (cfg->sd == 4) {
+        LE_CUDA_CHECK(cudaFuncSetAttribute(general_td_update_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+        general_td_update_kernel<4, 2><<<n_lanes, kGThreads, tc::kSmemBytes, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, cfg->batch_size, loss, scratch, stride);
+    } else {
+        LE_CUDA_CHECK(cudaFuncSetAttribute(general_td_update_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+        general_td_update_kernel<6, 3><<<n_lanes, kGThreads, tc::kSmemBytes, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, cfg->batch_size, loss, scratch, stride);
+    }
     LE_CUDA_CHECK(cudaGetLastError());
     LE_CUDA_CHECK(cudaFreeAsync(scratch, st));
     return LE_OK;

@@ -11,6 +11,7 @@
 // the forward needs a CTA-wide reduction before the TD error and the backward seeds dA = dq*[a=a_r] - sum(dq)/(B*AD).
 #pragma once
 #include "le_inner_loop.cuh"
+#include "le_tc.cuh"
 
 namespace le {
 
@@ -26,7 +27,9 @@ struct GNet {
 };
 
 __host__ __device__ inline void gnet_add(GLayer* l, int in, int out, int act, int* p, int* y) {
-    l->in = in; l->out = out; l->act = act; l->w_off = *p; *p += in * out; l->b_off = *p; *p += out; l->y_off = *y; *y += out;
+    // activation columns of a layer start at a multiple of 4 floats: 16-byte aligned rows for the vector staging of the
+    // tensor-core GEMM (the parameter offsets follow torch's state_dict order and stay unpadded)
+    l->in = in; l->out = out; l->act = act; l->w_off = *p; *p += in * out; l->b_off = *p; *p += out; l->y_off = *y; *y += (out + 3) & ~3;
 }
 // same construction as oracle/le_oracle.c build_net (torch state_dict order)
 __host__ __device__ inline void gnet_build(const le_lane_cfg* c, GNet* n) {
@@ -68,6 +71,20 @@ __device__ __forceinline__ float g_act_grad(int act, float slope, float h) {
     if (act == 1) return fmaf(-h, h, 1.f);
     if (act == 2) return h > 0.f ? 1.f : slope;
     return 1.f;
+}
+
+struct GActFn {
+    __device__ __forceinline__ float operator()(int act, float slope, float z) const { return g_act(act, slope, z); }
+};
+// Dense contractions (>= 64 rows, both other extents >= 32: the hidden x hidden layers of the dueling / two-hidden-layer
+// nets with the minibatch as rows, and their input / weight gradients) go to the tcgen05 tensor cores (le_tc.cuh, 3xTF32,
+// fp32 accumulate in TMEM); everything with a short side (first layers K = sd, heads N <= 4, row counts <= 16) stays on
+// the FFMA paths below.  `tcx` is null in kernels that do not own a TMEM allocation (TD3 lanes, single-row forward).
+#ifndef LE_GENERAL_TC
+#define LE_GENERAL_TC 1
+#endif
+__device__ __forceinline__ bool g_use_tc(const tc::Ctx* tcx, int I, int J, int L) {
+    return LE_GENERAL_TC && tcx != nullptr && I >= 64 && J >= 32 && L >= 32;
 }
 
 // C[i*c_si + j*c_sj] (+)= sum_l A[i*a_si + l*a_sl] * B[l*b_sl + j*b_sj]  (+ bias[j], activation)   — whole CTA.
@@ -306,28 +323,32 @@ static __device__ __noinline__ void g_thinj_fwd(const GLayer& l, const float* __
 }
 
 __device__ __forceinline__ void g_layer_fwd(const GLayer& l, const float* th, const float* X, int xs, int B, float* acts, int S,
-                                            float slope, float* sm) {
+                                            float slope, float* sm, tc::Ctx* tcx = nullptr) {
     if (B == 1) { g_thin_fwd<1>(l, th, X, xs, B, acts, S, slope, sm); return; }
     if (B <= 16) { g_thin_fwd<16>(l, th, X, xs, B, acts, S, slope, sm); return; }
     if (l.out <= 4) { g_thinj_fwd(l, th, X, xs, B, acts, S, slope, sm); return; }
+    if (g_use_tc(tcx, B, l.out, l.in)) {
+        tc::gemm_3xtf32(*tcx, X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, GActFn());
+        return;
+    }
     g_gemm(X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, sm);
 }
 
 // all layers for B rows; returns nothing: activations are in `acts` (row stride S = net.sum_out)
-static __device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm) {
+static __device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm, tc::Ctx* tcx = nullptr) {
     const int S = n.sum_out;
     const float* in = X;
     int in_s = xs;
     for (int i = 0; i < n.nfeat; ++i) {
-        g_layer_fwd(n.feat[i], th, in, in_s, B, acts, S, n.slope, sm);
+        g_layer_fwd(n.feat[i], th, in, in_s, B, acts, S, n.slope, sm, tcx);
         in = acts + n.feat[i].y_off;
         in_s = S;
     }
     if (n.kind == LE_Q_DUELING) {
-        g_layer_fwd(n.val[0], th, in, S, B, acts, S, n.slope, sm);
-        g_layer_fwd(n.val[1], th, acts + n.val[0].y_off, S, B, acts, S, n.slope, sm);
-        g_layer_fwd(n.adv[0], th, in, S, B, acts, S, n.slope, sm);
-        g_layer_fwd(n.adv[1], th, acts + n.adv[0].y_off, S, B, acts, S, n.slope, sm);
+        g_layer_fwd(n.val[0], th, in, S, B, acts, S, n.slope, sm, tcx);
+        g_layer_fwd(n.val[1], th, acts + n.val[0].y_off, S, B, acts, S, n.slope, sm, tcx);
+        g_layer_fwd(n.adv[0], th, in, S, B, acts, S, n.slope, sm, tcx);
+        g_layer_fwd(n.adv[1], th, acts + n.adv[0].y_off, S, B, acts, S, n.slope, sm, tcx);
     }
 }
 
@@ -366,7 +387,7 @@ static __device__ void g_q_values(const GNet& n, const float* acts, int B, float
 // backward of one dense layer for B rows. dact holds dL/dY at l.y_off (overwritten by dZ); X/xs: the layer's input.
 // dX (may be null) receives / accumulates dL/dX with row stride dxs.
 static __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const float* X, int xs, const float* acts, float* dact,
-                            int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm) {
+                            int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm, tc::Ctx* tcx = nullptr) {
     // dZ = dY * act'(Y) in place, and db[o] = sum_b dZ[b][o]: thread (rg, o) walks rows rg, rg+RG, ... of column o
     // (coalesced across o, independent loads down the column), partial sums meet in shared memory in fixed order.
     for (int o0 = 0; o0 < l.out; o0 += kGThreads) {
@@ -405,10 +426,18 @@ static __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad
         __syncthreads();
     }
     // dW[o][i] = sum_b dZ[b][o] * X[b][i]; the longer of (out, in) takes the 128-row side of the tile
-    if (l.out >= l.in) g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
+    const bool tc_dw = g_use_tc(tcx, B, l.out, l.in);     // (rows of the contraction = B, extents out x in)
+    if (tc_dw) {
+        if (l.out >= l.in) tc::gemm_3xtf32(*tcx, dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, GActFn());
+        else tc::gemm_3xtf32(*tcx, X, 1, xs, dact + l.y_off, S, 1, grad + l.w_off, 1, l.in, l.in, l.out, B, nullptr, 0, 0.f, false, GActFn());
+    } else if (l.out >= l.in) g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
     else g_gemm(X, 1, xs, dact + l.y_off, S, 1, grad + l.w_off, 1, l.in, l.in, l.out, B, nullptr, 0, 0.f, false, sm);
     // dX[b][i] (+)= sum_o dZ[b][o] * W[o][i]
-    if (dX) g_gemm(dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, sm);
+    if (dX) {
+        if (g_use_tc(tcx, B, l.in, l.out))
+            tc::gemm_3xtf32(*tcx, dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, GActFn());
+        else g_gemm(dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, sm);
+    }
 }
 
 // Device-side view of one lane slot's workspace
@@ -418,13 +447,13 @@ struct GSlot {
 };
 
 // DDQN.learn / DuelingDDQN.learn on the B rows staged in slot.xs / xs2 / misc (misc = [a, r, d, pad] per row)
-static __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red) {
+static __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red, tc::Ctx* tcx = nullptr) {
     const int S = n.sum_out, AD = n.ad, SDs = n.sd;
-    g_net_forward(n, w.theta, w.xs, SDs, B, w.actA, sm);    // q_values = model(states)            (activations kept)
+    g_net_forward(n, w.theta, w.xs, SDs, B, w.actA, sm, tcx);    // q_values = model(states)            (activations kept)
     g_q_values(n, w.actA, B, w.q, red);
-    g_net_forward(n, w.theta, w.xs2, SDs, B, w.actB, sm);   // next_q_values = model(next_states)
+    g_net_forward(n, w.theta, w.xs2, SDs, B, w.actB, sm, tcx);   // next_q_values = model(next_states)
     g_q_values(n, w.actB, B, w.q2, red);
-    g_net_forward(n, w.thetaT, w.xs2, SDs, B, w.actB, sm);  // model_target(next_states)
+    g_net_forward(n, w.thetaT, w.xs2, SDs, B, w.actB, sm, tcx);  // model_target(next_states)
     g_q_values(n, w.actB, B, w.qT, red);
     float lpart = 0.f, gpart = 0.f;
     for (int b = threadIdx.x; b < B; b += kGThreads) {
@@ -460,16 +489,16 @@ static __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnS
     __syncthreads();
     const GLayer& lf = n.feat[n.nfeat - 1];
     if (n.kind == LE_Q_DUELING) {
-        g_layer_bwd(n.val[1], w.theta, w.grad, w.actA + n.val[0].y_off, S, w.actA, w.dact, S, B, w.dact + n.val[0].y_off, S, false, n.slope, sm);
-        g_layer_bwd(n.val[0], w.theta, w.grad, w.actA + lf.y_off, S, w.actA, w.dact, S, B, w.dact + lf.y_off, S, false, n.slope, sm);
-        g_layer_bwd(n.adv[1], w.theta, w.grad, w.actA + n.adv[0].y_off, S, w.actA, w.dact, S, B, w.dact + n.adv[0].y_off, S, false, n.slope, sm);
-        g_layer_bwd(n.adv[0], w.theta, w.grad, w.actA + lf.y_off, S, w.actA, w.dact, S, B, w.dact + lf.y_off, S, true, n.slope, sm);
+        g_layer_bwd(n.val[1], w.theta, w.grad, w.actA + n.val[0].y_off, S, w.actA, w.dact, S, B, w.dact + n.val[0].y_off, S, false, n.slope, sm, tcx);
+        g_layer_bwd(n.val[0], w.theta, w.grad, w.actA + lf.y_off, S, w.actA, w.dact, S, B, w.dact + lf.y_off, S, false, n.slope, sm, tcx);
+        g_layer_bwd(n.adv[1], w.theta, w.grad, w.actA + n.adv[0].y_off, S, w.actA, w.dact, S, B, w.dact + n.adv[0].y_off, S, false, n.slope, sm, tcx);
+        g_layer_bwd(n.adv[0], w.theta, w.grad, w.actA + lf.y_off, S, w.actA, w.dact, S, B, w.dact + lf.y_off, S, true, n.slope, sm, tcx);
     }
     for (int i = n.nfeat - 1; i >= 0; --i) {
         const GLayer& l = n.feat[i];
         const float* X = i > 0 ? w.actA + n.feat[i - 1].y_off : w.xs;
         const int xs = i > 0 ? S : SDs;
-        g_layer_bwd(l, w.theta, w.grad, X, xs, w.actA, w.dact, S, B, i > 0 ? w.dact + n.feat[i - 1].y_off : nullptr, S, false, n.slope, sm);
+        g_layer_bwd(l, w.theta, w.grad, X, xs, w.actA, w.dact, S, B, i > 0 ? w.dact + n.feat[i - 1].y_off : nullptr, S, false, n.slope, sm, tcx);
     }
     // Adam + Polyak (same operation order as LaneCore::adam_polyak)
     ls.b1pow *= ls.beta1;
@@ -581,15 +610,20 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
     __shared__ int sred[kGThreads / 32];
     __shared__ le_lane_cfg cfg_sm;
     __shared__ GNet net_sm;          // this lane's network (per-lane q_hidden / q_layers under vary_hp)
+    extern __shared__ __align__(128) unsigned char tc_smem[];   // tc::kSmemBytes: operand parts of the tensor-core GEMM
+    tc::Ctx tcs = tc::ctx_create(tc_smem);
+    tc::Ctx* const tcx = &tcs;
     const RunParams& P = G.rp;
     const GNet& n = net_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const GSlot w = gslot_view(G.slots + (int64_t)blockIdx.x * G.slot_stride, G.net, P.ring_cap, RL::ROWF, G.bmax);   // sized for the maxima (cfg 0)
+    bool first_lane = true;   // the first lane of a CTA slot is static (lane_id == slot), the rest come from the queue counter
     for (;;) {
         __syncthreads();
-        if (tid == 0) ibox[0] = atomicAdd(P.work_counter, 1);
+        if (tid == 0) ibox[0] = first_lane ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(P.work_counter, 1);
         __syncthreads();
         const int lane_id = ibox[0];
+        first_lane = false;
         if (lane_id >= P.n_lanes) break;
         {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(P.cfg + (P.n_cfg == 1 ? 0 : lane_id));
@@ -796,7 +830,7 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
                         w.misc[4 * b] = (float)__float_as_int(rowv[RL::OFF_A]); w.misc[4 * b + 1] = rowv[RL::OFF_R]; w.misc[4 * b + 2] = rowv[RL::OFF_D];
                     }
                     __syncthreads();
-                    loss = g_td_update(n, w, B, ls, sm, red);
+                    loss = g_td_update(n, w, B, ls, sm, red, tcx);
                     learn_iters += 1;
                 }
                 if (tracing && train_steps < P.trace.cap && tid == 0) {
@@ -839,6 +873,7 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
             P.out[lane_id] = o;
         }
     }
+    tc::ctx_destroy(tcs);
 }
 
 // unit kernels on caller-owned canonical arrays (same layout as the slot's theta/thetaT/m/v)
@@ -849,6 +884,8 @@ general_td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, GNet n, float*
                          int64_t scratch_stride) {
     __shared__ __align__(16) float sm[kGSmemFloats];
     __shared__ float red[32];
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    tc::Ctx tcs = tc::ctx_create(tc_smem);
     const int id = blockIdx.x, tid = threadIdx.x;
     const le_lane_cfg c = *cfg_dev;
     int64_t offs[18];
@@ -876,8 +913,9 @@ general_td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, GNet n, float*
     const int t0 = tcount[id];
     ls.b1pow = pow(c.beta1, (double)t0);
     ls.b2pow = pow(c.beta2, (double)t0);
-    const float loss = g_td_update(n, w, B, ls, sm, red);
+    const float loss = g_td_update(n, w, B, ls, sm, red, &tcs);
     if (tid == 0) { loss_out[id] = loss; tcount[id] = t0 + 1; }
+    tc::ctx_destroy(tcs);
 }
 
 template <int SD, int AD>

@@ -40,16 +40,18 @@ template <int U> constexpr int inner_warps() { return U <= 2 ? kWarpsPerCta : LE
 template <int SD, int AD, int U>
 struct SmemWarp {
     using SL = StageLayout<SD>;
-    static constexpr int PUP = ((SD + 1 + AD) + 3) / 4 * 4;  // padded per-unit record of the test-phase weight image
+    static constexpr int PUP = SD + 1 + AD;           // per-unit record of the test-phase weight image (scalar reads, broadcast)
     static constexpr int STAGE_ONE_F = SL::ROWS * SL::STAGE_F;
     static constexpr int STAGE_F = 2 * STAGE_ONE_F;   // double buffer: the gather of round k+1 overlaps the compute of round k
-    static constexpr int QW_F = U * 32 * PUP;
+    static constexpr int QW_F = (U * 32 * PUP + 3) / 4 * 4;
     static constexpr int BUF_F = STAGE_F > QW_F ? STAGE_F : QW_F;
     static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
     static constexpr int CFG_F = (sizeof(le_lane_cfg) + 15) / 16 * 4;
-    static constexpr int RED_F = 2 * (U <= 2 ? LE_R_U2 : 4) * (1 + AD) * 32 * 2;  // LaneCore::RED_F: two cross-lane reduction buffers
+    static constexpr int RED_R = (U <= 2 ? LE_R_U2 : 4);
+    static constexpr int RED_F = ((LE_PIPELINED || LE_DQ_SHFL) ? 2 : 1) * (RED_R * (((AD + 1) / 2 + AD + 1) / 2) * 32 * 4 + RED_R * 4);  // LaneCore::RED_F + DQS_F
     static constexpr int FLOATS = BUF_F + MV_F + CFG_F + RED_F;
     static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F, OFF_RED = BUF_F + MV_F + CFG_F;
+    static_assert(FLOATS % 4 == 0 && OFF_RED % 4 == 0 && STAGE_ONE_F % 4 == 0, "float4 accesses of the stage / reduction buffer need 16-byte alignment");
 };
 
 __device__ __forceinline__ float4 ld_cg_f4(const float4* p) { return __ldcg(p); }
@@ -95,10 +97,10 @@ struct FusedLane {
         for (int u = 0; u < U; ++u) {
             float* rec = smem + (lane + 32 * u) * PUP;
 #pragma unroll
-            for (int i = 0; i < SD; ++i) rec[i] = core.wt1[u][i].x;
-            rec[SD] = core.bt1[u].x;
+            for (int i = 0; i < SD; ++i) rec[i] = core.w1_on(u, i);
+            rec[SD] = core.b1_on(u);
 #pragma unroll
-            for (int a = 0; a < AD; ++a) rec[SD + 1 + a] = core.wt2[u][a].x;
+            for (int a = 0; a < AD; ++a) rec[SD + 1 + a] = core.w2_on(u, a);
         }
         __syncwarp();
         const int H = c.q_hidden;
@@ -376,10 +378,16 @@ __global__ void __launch_bounds__(inner_warps<U>() * 32, (U <= 2 ? LE_MIN_CTAS_U
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * inner_warps<U>() + warp;
     float* smem = smem_dyn + warp * SW::FLOATS;
+    // Lane queue: the first lane of every warp slot is static (lane_id == slot, so with n_lanes <= slots a lane's replay ring
+    // is the ring of slot lane_id: agents.py reads it back), every further lane comes from the global counter.
+    bool first = true;
     for (;;) {
-        int lane_id = 0;
-        if (lane == 0) lane_id = atomicAdd(P.work_counter, 1);
-        lane_id = __shfl_sync(LE_FULL_MASK, lane_id, 0);
+        int lane_id = slot;
+        if (!first) {
+            if (lane == 0) lane_id = (int)(gridDim.x * inner_warps<U>()) + atomicAdd(P.work_counter, 1);
+            lane_id = __shfl_sync(LE_FULL_MASK, lane_id, 0);
+        }
+        first = false;
         if (lane_id >= P.n_lanes) break;
         FusedLane<SD, AD, U, ACT>::run(P, lane_id, slot, smem, lane);
         __syncwarp();

@@ -1,8 +1,9 @@
-// le_inst_cp_leaky.cu — compiled kernel set for SD=4, AD=2, QACT_LEAKY, units per thread {2,4} (Q-net hidden <= 32*U).
+// le_inst_cp_leaky.cu — compiled kernel set for SD=4, AD=2, QACT_LEAKY, units per thread {2,4,6} (Q-net hidden <= 32*U: up to 192, the DDQN_vary range [19,171]).
 #include "le_instance.cuh"
 namespace le {
 void le_register_cp_leaky() {
     le_register_instance(InstanceImpl<4, 2, 2, QACT_LEAKY>::ops());
     le_register_instance(InstanceImpl<4, 2, 4, QACT_LEAKY>::ops());
+    le_register_instance(InstanceImpl<4, 2, 6, QACT_LEAKY>::ops());
 }
 }  // namespace le

@@ -114,6 +114,21 @@ def td_update(cfg, q_theta, q_target, adam_m, adam_v, adam_t, rows):
     return loss
 
 
+def tc_gemm(A, B, C_out, form, I, J, L, bias=None, act=0, slope=0.0, accumulate=False):
+    """One dense-layer GEMM on the tcgen05 tensor cores (3xTF32): `form` names the nn.Linear contraction
+         "nt": C[I,J] = A[I,L] @ B[J,L]^T   (forward  Y = X W^T, + bias, activation)
+         "nn": C[I,J] = A[I,L] @ B[L,J]     (input gradient  dX = dZ W)
+         "tn": C[I,J] = A[L,I]^T @ B[L,J]   (weight gradient dW = dZ^T X)
+    on row-major contiguous CUDA tensors; C_out is written (or accumulated into) in place."""
+    a_si, a_sl = (A.shape[1], 1) if form in ("nt", "nn") else (1, A.shape[1])
+    b_sl, b_sj = (1, B.shape[1]) if form == "nt" else (B.shape[1], 1)
+    check(_lib().le_tc_gemm(_ptr(_dev(A, _F32)), C.c_int(a_si), C.c_int(a_sl), _ptr(_dev(B, _F32)), C.c_int(b_sl), C.c_int(b_sj),
+                            _ptr(_dev(C_out, _F32)), C.c_int(C_out.shape[1]), C.c_int(1), C.c_int(I), C.c_int(J), C.c_int(L),
+                            _ptr(bias) if bias is not None else None, C.c_int(act), C.c_float(slope), C.c_int(1 if accumulate else 0), _stream()),
+          "le_tc_gemm")
+    return C_out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def inner_loop_plan(cfg, n_lanes, n_env=1):
     g, s, r, u, o = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()

@@ -51,6 +51,26 @@ def _max_cfg(cfgs):
     return m
 
 
+def launch_groups(cfgs, indices=None):
+    """Splits lanes into one launch per kernel family and orders every launch's lane queue longest-first.
+
+    Families: the warp-per-lane register kernel sets by hidden units per thread (U = 2: hidden_size <= 64, U = 4: <= 128,
+    U = 6: <= 192, CartPole shapes) — a lane with 40 hidden units should not pay for the 128-unit kernel of its neighbour — and
+    the general CTA-per-lane kernel for everything else (two hidden layers, wider nets).  Inside a launch the persistent
+    kernel hands out lanes in queue order, so the most expensive lanes (cost ~ batch_size x parameters) go first and the
+    cheap ones fill the ragged tail.  Returns a list of index arrays into `cfgs`."""
+    idx_all = np.arange(len(cfgs)) if indices is None else np.asarray(indices)
+    fam = {}
+    for i in idx_all:
+        fam.setdefault(cfgs[i].register_units(), []).append(int(i))
+    out = []
+    for u in sorted(fam, key=lambda k: (k == 0, k)):       # register families first, the general kernel last
+        idx = np.asarray(fam[u])
+        cost = np.array([cfgs[i].batch_size * cfgs[i].q_params() for i in idx], np.float64)
+        out.append(idx[np.argsort(-cost, kind="stable")])
+    return out
+
+
 def _run_group(sub, cfg0, theta, env_index, keys, n_env, device):
     """One launch of the fused kernel for lanes that share a kernel family.  Returns (final test rewards [k, T] f64,
     training agent steps [k], episodes [k]) as numpy arrays.  (the CPU host-logic tests substitute their own launch function.)"""
@@ -99,13 +119,7 @@ def evaluate_agents(config, env_thetas, agents_num=10, seed=0, overrides=None, v
     lo, hi = n * rank // world, n * (rank + 1) // world
     T = max(c.test_episodes for c in cfgs)
     table = np.zeros((n, T + 2), np.float64)      # [test rewards | train steps | episodes] per lane; zero outside this rank's block
-    groups = {True: [], False: []}
-    for i in range(lo, hi):
-        groups[cfgs[i].q_is_register_resident()].append(i)
-    for resident, idx in groups.items():
-        if not idx:
-            continue
-        idx = np.asarray(idx)
+    for idx in launch_groups(cfgs, np.arange(lo, hi)):
         sub = [cfgs[i] for i in idx]
         env_index = None if theta is None or n_env == 1 else env_of[idx]
         tr, st, ep = _run_group(sub, _max_cfg(sub), theta, env_index, keys[idx], n_env, device)

@@ -21,8 +21,22 @@ import contextlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("LE_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "stubs")
+
+
+def _reference_root():
+    """LE_REFERENCE_ROOT, else /root/reference (build container), else the byte-for-byte copy staged by oracle/make_ref.py
+    under the git-ignored oracle/_ref/pyref (the only form in which the reference reaches the GPU box)."""
+    env = os.environ.get("LE_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/agents"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref", "pyref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available():
