@@ -45,6 +45,8 @@ WORKLOADS = {
     "cartpole_se_dueling": dict(cfg="cartpole_syn_env", kind="se", agent="duelingddqn", members_per_gpu=296, train_episodes=3),
     # 197 members x 3 lanes = 591 lanes = two full waves of the 296 resident CTAs
     "acrobot_se_dueling": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=197, train_episodes=2, init_episodes=1),
+    # the same with the dense hidden x hidden layers on the tcgen05 tensor cores (LE_TC=1: 3xTF32, TMEM accumulators, one CTA per SM)
+    "acrobot_se_dueling_tc": dict(cfg="acrobot_syn_env", kind="se", agent="duelingddqn", members_per_gpu=197, train_episodes=2, init_episodes=1, tc=True),
     # BASELINE config 4 (vary_hp evaluation): 4096 DDQN agents per GPU with per-lane lr / batch_size / hidden_size / hidden_layer
     # on ONE fixed CartPole SE, init_episodes=10, plateau early-out; train_episodes bounded (the evaluator's cap is 1000)
     "vary_hp": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=4096, train_episodes=30),
@@ -52,7 +54,8 @@ WORKLOADS = {
     # (50 200 rows x 48 B x 1776 slots): the random 48-byte gathers come from HBM, not from the 126 MB L2
     "cartpole_se_fullring": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=500, step_budget=50000),
 }
-EXTRA_WORKLOADS = ["acrobot_se", "cartpole_rn", "cartpole_se_dueling", "acrobot_se_dueling", "sweep_h1024", "cartpole_se_fullring", "vary_hp"]
+EXTRA_WORKLOADS = ["acrobot_se", "cartpole_rn", "cartpole_se_dueling", "acrobot_se_dueling", "acrobot_se_dueling_tc", "sweep_h1024",
+                   "cartpole_se_fullring", "vary_hp"]
 STRONG_POPULATION = 8 * 1184
 
 
@@ -431,6 +434,7 @@ def measure_nes(D, workload, steps, warmup, members_per_gpu=0, population=0, lan
     from learning_environments_b200.rng import lane_keys
     dist, dev, world, rank = D.dist, D.dev, D.world, D.rank
     d, cfg = build_lane_cfg(workload)
+    os.environ["LE_TC"] = "1" if WORKLOADS[workload].get("tc") else "0"     # read by the library at plan / launch time
     for ov in lane_override:
         k, v = ov.split("=")
         setattr(cfg, k, type(getattr(cfg, k))(float(v)))
@@ -565,6 +569,7 @@ def measure_nes(D, workload, steps, warmup, members_per_gpu=0, population=0, lan
         res["nes_generations_per_hour"] = 3600.0 / (mx[0] / max(steps, 1))
     del ev
     torch.cuda.empty_cache()
+    os.environ["LE_TC"] = "0"
     return res, cfg
 
 

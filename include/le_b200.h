@@ -118,6 +118,9 @@ typedef struct le_trace {
     float* reward;          /* [cap]                                                                   */
     float* done;            /* [cap]                                                                   */
     float* loss;            /* [cap] NaN when no learn() happened on that step                         */
+    float* qgap;            /* NULL or [cap]: greedy steps: (q_best - q_second) / max(|q_best|, |q_second|, 1e-12) of the
+                               Q-values the action was chosen from (a near-tie marker for the parity tests); NaN when the
+                               action was random                                                         */
 } le_trace;
 
 /* ------------------------------------------------------------------------------------------------ */

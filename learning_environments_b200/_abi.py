@@ -108,7 +108,7 @@ class Trace(C.Structure):
     _fields_ = [
         ("cap", C.c_int32),
         ("action", C.c_void_p), ("explore", C.c_void_p), ("next_state", C.c_void_p),
-        ("reward", C.c_void_p), ("done", C.c_void_p), ("loss", C.c_void_p),
+        ("reward", C.c_void_p), ("done", C.c_void_p), ("loss", C.c_void_p), ("qgap", C.c_void_p),
     ]
 
 

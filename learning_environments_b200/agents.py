@@ -241,6 +241,14 @@ class DDQN(BaseAgent):
             while len(lengths) < self.train_episodes:
                 lengths.append(max(lengths))
         self._theta.copy_(bufs.q_final[0])
+        # The kernel returns the trained ONLINE net only.  The reference keeps target net / Adam moments / eps on the agent
+        # object across calls; a fresh agent per calc_score is its only usage on this path (agents/GTN_worker.py:190), so the
+        # step-by-step API continues from a re-synchronised state: target <- online (the Polyak lag of tau per step is not
+        # carried over), Adam moments zero, eps advanced to the value after the episodes just run (agents/DDQN.py:112-117).
+        if hasattr(self, "_target"):
+            self._target.copy_(self._theta)
+        if n > 0 and hasattr(self, "eps"):
+            self.eps = max(float(self.eps_init) * float(self.eps_decay) ** (n - 1), float(self.eps_min))
         self.it += int(out["learn_iters"])
         self.last_run = dict(out=out, cfg=cfg)
         rb = self._replay_from_ring(bufs, cfg, int(out["train_steps"]))

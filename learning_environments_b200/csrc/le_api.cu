@@ -313,6 +313,16 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
 
 using namespace le;
 
+// Owns the private stream and the device arena of a *_host entry point: every early return (LE_CUDA_CHECK) releases both.
+struct HostCall {
+    cudaStream_t st = nullptr;
+    char* arena = nullptr;
+    ~HostCall() {
+        if (arena) cudaFreeAsync(arena, st);
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    }
+};
+
 extern "C" {
 
 int le_version(void) { return LE_VERSION; }
@@ -540,8 +550,9 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
     const int P_env = c->env_kind == LE_ENV_SE ? 3 * c->env_hidden * (c->sd + c->ad + 1) + c->env_hidden * (c->sd + 2) + c->sd + 2
                                               : (c->env_kind == LE_ENV_RN ? c->env_hidden * (c->sd + 2) + 1 : 0);
     const int rs = c->train_episodes > 0 ? c->train_episodes : 1;
-    cudaStream_t st;
-    LE_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HostCall hc;
+    LE_CUDA_CHECK(cudaStreamCreateWithFlags(&hc.st, cudaStreamNonBlocking));
+    cudaStream_t st = hc.st;
     // one device arena for every array of the call
     struct Seg { const void* src; void* dst_host; size_t bytes; size_t off; };
     std::vector<Seg> segs;
@@ -559,8 +570,8 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
     const size_t i_tr = add(nullptr, test_rewards, sizeof(double) * (size_t)c->test_episodes * n_lanes);
     const size_t off_ws = total;
     total += (size_t)pl.total_bytes;
-    char* arena = nullptr;
-    LE_CUDA_CHECK(cudaMallocAsync((void**)&arena, total, st));
+    LE_CUDA_CHECK(cudaMallocAsync((void**)&hc.arena, total, st));
+    char* arena = hc.arena;
     for (auto& s : segs)
         if (s.src && s.bytes) LE_CUDA_CHECK(cudaMemcpyAsync(arena + s.off, s.src, s.bytes, cudaMemcpyHostToDevice, st));
     LE_CUDA_CHECK(cudaMemsetAsync(arena + segs[i_rw].off, 0, segs[i_rw].bytes + segs[i_ln].bytes, st));
@@ -577,10 +588,7 @@ int le_inner_loop_run_host(const le_lane_cfg* cfgs, int n_cfg, const float* env_
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == LE_OK) { le_set_error("le_inner_loop_run_host: %s", cudaGetErrorString(e)); rc = LE_ECUDA; }
-    cudaFreeAsync(arena, st);
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
-    return rc;
+    return rc;   // ~HostCall frees the arena and destroys the stream
 }
 
 // ---- TD3_discrete_vary lanes ----------------------------------------------------------------------------
@@ -627,8 +635,9 @@ int le_td3_run_host(const le_td3_cfg* cfg, const float* env_theta, int n_env, co
     const int64_t pack_stride_f = (c->env_kind == LE_ENV_SE ? ops->se_pack_vec4(c->env_hidden) : 1) * 4;
     const int rs = c->train_episodes > 0 ? c->train_episodes : 1;
     const int tcap = trace_host ? trace_host->cap : 0;
-    cudaStream_t st;
-    LE_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HostCall hc;
+    LE_CUDA_CHECK(cudaStreamCreateWithFlags(&hc.st, cudaStreamNonBlocking));
+    cudaStream_t st = hc.st;
     struct Seg { const void* src; void* dst_host; size_t bytes; size_t off; };
     std::vector<Seg> segs;
     size_t total = 0;
@@ -656,8 +665,8 @@ int le_td3_run_host(const le_td3_cfg* cfg, const float* env_theta, int n_env, co
     total += 256;
     const size_t off_slots = total;
     total += (size_t)tp.grid * tp.slot_floats * sizeof(float);
-    char* arena = nullptr;
-    LE_CUDA_CHECK(cudaMallocAsync((void**)&arena, total, st));
+    LE_CUDA_CHECK(cudaMallocAsync((void**)&hc.arena, total, st));
+    char* arena = hc.arena;
     for (auto& s : segs)
         if (s.src && s.bytes) LE_CUDA_CHECK(cudaMemcpyAsync(arena + s.off, s.src, s.bytes, cudaMemcpyHostToDevice, st));
     LE_CUDA_CHECK(cudaMemsetAsync(arena + segs[i_rw].off, 0, segs[i_rw].bytes + segs[i_ln].bytes, st));
@@ -695,10 +704,7 @@ int le_td3_run_host(const le_td3_cfg* cfg, const float* env_theta, int n_env, co
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == LE_OK) { le_set_error("le_td3_run_host: %s", cudaGetErrorString(e)); rc = LE_ECUDA; }
-    cudaFreeAsync(arena, st);
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
-    return rc;
+    return rc;   // ~HostCall frees the arena and destroys the stream
 }
 
 // ---- NES ----------------------------------------------------------------------------------------------

@@ -1,20 +1,40 @@
 // le_general.cu — host side of the CTA-per-lane general Q-network kernels (le_general.cuh).
+#include <cstdio>
+#include <cstdlib>
 #include "le_general.cuh"
 #include "le_general_api.h"
 
 namespace le {
 
+// LE_TC=1 in the environment selects the tensor-core instantiations of the CTA-per-lane kernels (dense hidden x hidden layers
+// on tcgen05 / TMEM, le_tc.cuh).  Default: the FFMA instantiations — measured faster at the reference's layer sizes (60 .. 128
+// wide, 128 .. 193 rows): a TMEM-allocating kernel is held to one CTA per SM and the per-GEMM operand split / staging is not
+// amortised by 128^3 contractions (profiles/r02_general_tc.txt).
+bool general_use_tc() {
+    const char* e = getenv("LE_TC");
+    return e && e[0] == '1';
+}
+
+template <int SD, int AD, bool TC>
+static int occupancy_of(int* nb) {
+    const size_t dyn = TC ? tc::kSmemBytes : 0;
+    cudaError_t e = cudaSuccess;
+    if (TC) e = cudaFuncSetAttribute(general_loop_kernel<SD, AD, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, general_loop_kernel<SD, AD, TC>, kGThreads, dyn);
+    if (getenv("LE_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, general_loop_kernel<SD, AD, TC>);
+        fprintf(stderr, "[le] general kernel<%d,%d,tc=%d> occupancy: %d CTAs/SM (%s; regs %d, static smem %zu B, dynamic %zu B, local %zu B)\n", SD, AD,
+                (int)TC, *nb, cudaGetErrorString(e), fa.numRegs, fa.sharedSizeBytes, dyn, fa.localSizeBytes);
+    }
+    return e == cudaSuccess ? 0 : -1;
+}
+
 static int general_occupancy(int sd) {
     int nb = 0;
-    // dynamic shared memory = the operand parts of the tcgen05 GEMM (le_tc.cuh); two CTAs per SM also bound the TMEM use
-    // (2 x 128 of the SM's 512 accumulator columns)
-    if (sd == 4) {
-        cudaFuncSetAttribute(general_loop_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, general_loop_kernel<4, 2>, kGThreads, tc::kSmemBytes);
-    } else {
-        cudaFuncSetAttribute(general_loop_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, general_loop_kernel<6, 3>, kGThreads, tc::kSmemBytes);
-    }
+    const bool tcp = general_use_tc();
+    if (sd == 4) { if (tcp) occupancy_of<4, 2, true>(&nb); else occupancy_of<4, 2, false>(&nb); }
+    else { if (tcp) occupancy_of<6, 3, true>(&nb); else occupancy_of<6, 3, false>(&nb); }
     if (nb > 2) nb = 2;
     return nb < 1 ? 1 : nb;
 }
@@ -35,6 +55,17 @@ int general_plan(const le_lane_cfg* c, int n_lanes, int ring_cap, int sms, Gener
     return LE_OK;
 }
 
+template <int SD, int AD, bool TC>
+static cudaError_t launch_loop(const GRunParams& G, int grid, cudaStream_t st) {
+    const size_t dyn = TC ? tc::kSmemBytes : 0;
+    if (TC) {
+        cudaError_t e = cudaFuncSetAttribute(general_loop_kernel<SD, AD, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+    }
+    general_loop_kernel<SD, AD, TC><<<grid, kGThreads, dyn, st>>>(G);
+    return cudaGetLastError();
+}
+
 cudaError_t general_launch(const le_lane_cfg* c, const RunParams& rp, float* slots, const GeneralPlan& gp, cudaStream_t st) {
     GRunParams G;
     G.rp = rp;
@@ -42,11 +73,20 @@ cudaError_t general_launch(const le_lane_cfg* c, const RunParams& rp, float* slo
     G.slots = slots;
     G.slot_stride = gp.slot_floats;
     G.bmax = gp.bmax;
-    cudaError_t e = c->sd == 4 ? cudaFuncSetAttribute(general_loop_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)
-                               : cudaFuncSetAttribute(general_loop_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    if (c->sd == 4) general_loop_kernel<4, 2><<<gp.grid, kGThreads, tc::kSmemBytes, st>>>(G);
-    else general_loop_kernel<6, 3><<<gp.grid, kGThreads, tc::kSmemBytes, st>>>(G);
+    const bool tcp = general_use_tc();
+    if (c->sd == 4) return tcp ? launch_loop<4, 2, true>(G, gp.grid, st) : launch_loop<4, 2, false>(G, gp.grid, st);
+    return tcp ? launch_loop<6, 3, true>(G, gp.grid, st) : launch_loop<6, 3, false>(G, gp.grid, st);
+}
+
+template <int SD, int AD, bool TC>
+static cudaError_t launch_td(const le_lane_cfg* cfg_dev, const GNet& n, float* th, float* thT, float* m, float* v, int32_t* t, int n_lanes,
+                             const float* rows, int B, float* loss, float* scratch, int64_t stride, cudaStream_t st) {
+    const size_t dyn = TC ? tc::kSmemBytes : 0;
+    if (TC) {
+        cudaError_t e = cudaFuncSetAttribute(general_td_update_kernel<SD, AD, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+    }
+    general_td_update_kernel<SD, AD, TC><<<n_lanes, kGThreads, dyn, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, B, loss, scratch, stride);
     return cudaGetLastError();
 }
 
@@ -58,14 +98,14 @@ int general_td_update(const le_lane_cfg* cfg, const le_lane_cfg* cfg_dev, float*
     const int64_t stride = gslot_floats(n, 0, 0, cfg->batch_size, offs);
     float* scratch = nullptr;
     LE_CUDA_CHECK(cudaMallocAsync((void**)&scratch, (size_t)stride * 4 * n_lanes, st));
-    if (cfg->sd == 4) {
-        LE_CUDA_CHECK(cudaFuncSetAttribute(general_td_update_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-        general_td_update_kernel<4, 2><<<n_lanes, kGThreads, tc::kSmemBytes, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, cfg->batch_size, loss, scratch, stride);
-    } else {
-        LE_CUDA_CHECK(cudaFuncSetAttribute(general_td_update_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-        general_td_update_kernel<6, 3><<<n_lanes, kGThreads, tc::kSmemBytes, st>>>(cfg_dev, n, th, thT, m, v, t, n.P, rows, cfg->batch_size, loss, scratch, stride);
-    }
-    LE_CUDA_CHECK(cudaGetLastError());
+    const bool tcp = general_use_tc();
+    const int B = cfg->batch_size;
+    cudaError_t le;
+    if (cfg->sd == 4) le = tcp ? launch_td<4, 2, true>(cfg_dev, n, th, thT, m, v, t, n_lanes, rows, B, loss, scratch, stride, st)
+                               : launch_td<4, 2, false>(cfg_dev, n, th, thT, m, v, t, n_lanes, rows, B, loss, scratch, stride, st);
+    else le = tcp ? launch_td<6, 3, true>(cfg_dev, n, th, thT, m, v, t, n_lanes, rows, B, loss, scratch, stride, st)
+                  : launch_td<6, 3, false>(cfg_dev, n, th, thT, m, v, t, n_lanes, rows, B, loss, scratch, stride, st);
+    LE_CUDA_CHECK(le);
     LE_CUDA_CHECK(cudaFreeAsync(scratch, st));
     return LE_OK;
 }

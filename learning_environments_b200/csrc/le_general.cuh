@@ -10,6 +10,8 @@
 // Dueling coupling (models/actor_critic.py:121): q = V + (A - A.mean()) with the mean over the WHOLE batch tensor, so
 // the forward needs a CTA-wide reduction before the TD error and the backward seeds dA = dq*[a=a_r] - sum(dq)/(B*AD).
 #pragma once
+#include <cstddef>
+#include <type_traits>
 #include "le_inner_loop.cuh"
 #include "le_tc.cuh"
 
@@ -83,8 +85,17 @@ struct GActFn {
 #ifndef LE_GENERAL_TC
 #define LE_GENERAL_TC 1
 #endif
-__device__ __forceinline__ bool g_use_tc(const tc::Ctx* tcx, int I, int J, int L) {
-    return LE_GENERAL_TC && tcx != nullptr && I >= 64 && J >= 32 && L >= 32;
+// TCX is tc::Ctx* in the tensor-core instantiations of the lane kernels and std::nullptr_t everywhere else: kernels that do
+// not own a TMEM allocation contain no tcgen05 code at all (a kernel that allocates TMEM is limited to ONE resident CTA per SM
+// by the runtime, measured with tools/ubench/occ_tmem.cu, so the FFMA instantiations keep their two CTAs per SM).
+template <typename TCX>
+__device__ __forceinline__ bool g_use_tc(TCX tcx, int I, int J, int L) {
+    if constexpr (std::is_same<TCX, tc::Ctx*>::value) return LE_GENERAL_TC && tcx != nullptr && I >= 64 && J >= 32 && L >= 32;
+    else return false;
+}
+template <typename TCX, typename... Args>
+__device__ __forceinline__ void g_tc_gemm(TCX tcx, Args... args) {
+    if constexpr (std::is_same<TCX, tc::Ctx*>::value) tc::gemm_3xtf32(*tcx, args..., GActFn());
 }
 
 // C[i*c_si + j*c_sj] (+)= sum_l A[i*a_si + l*a_sl] * B[l*b_sl + j*b_sj]  (+ bias[j], activation)   — whole CTA.
@@ -322,20 +333,22 @@ static __device__ __noinline__ void g_thinj_fwd(const GLayer& l, const float* __
     __syncthreads();
 }
 
+template <typename TCX = std::nullptr_t>
 __device__ __forceinline__ void g_layer_fwd(const GLayer& l, const float* th, const float* X, int xs, int B, float* acts, int S,
-                                            float slope, float* sm, tc::Ctx* tcx = nullptr) {
+                                            float slope, float* sm, TCX tcx = nullptr) {
     if (B == 1) { g_thin_fwd<1>(l, th, X, xs, B, acts, S, slope, sm); return; }
     if (B <= 16) { g_thin_fwd<16>(l, th, X, xs, B, acts, S, slope, sm); return; }
     if (l.out <= 4) { g_thinj_fwd(l, th, X, xs, B, acts, S, slope, sm); return; }
     if (g_use_tc(tcx, B, l.out, l.in)) {
-        tc::gemm_3xtf32(*tcx, X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, GActFn());
+        g_tc_gemm(tcx, X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false);
         return;
     }
     g_gemm(X, xs, 1, th + l.w_off, 1, l.in, acts + l.y_off, S, 1, B, l.out, l.in, th + l.b_off, l.act, slope, false, sm);
 }
 
 // all layers for B rows; returns nothing: activations are in `acts` (row stride S = net.sum_out)
-static __device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm, tc::Ctx* tcx = nullptr) {
+template <typename TCX = std::nullptr_t>
+static __device__ void g_net_forward(const GNet& n, const float* th, const float* X, int xs, int B, float* acts, float* sm, TCX tcx = nullptr) {
     const int S = n.sum_out;
     const float* in = X;
     int in_s = xs;
@@ -386,8 +399,9 @@ static __device__ void g_q_values(const GNet& n, const float* acts, int B, float
 
 // backward of one dense layer for B rows. dact holds dL/dY at l.y_off (overwritten by dZ); X/xs: the layer's input.
 // dX (may be null) receives / accumulates dL/dX with row stride dxs.
+template <typename TCX = std::nullptr_t>
 static __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad, const float* X, int xs, const float* acts, float* dact,
-                            int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm, tc::Ctx* tcx = nullptr) {
+                            int S, int B, float* dX, int dxs, bool dx_accumulate, float slope, float* sm, TCX tcx = nullptr) {
     // dZ = dY * act'(Y) in place, and db[o] = sum_b dZ[b][o]: thread (rg, o) walks rows rg, rg+RG, ... of column o
     // (coalesced across o, independent loads down the column), partial sums meet in shared memory in fixed order.
     for (int o0 = 0; o0 < l.out; o0 += kGThreads) {
@@ -428,14 +442,14 @@ static __device__ void g_layer_bwd(const GLayer& l, const float* th, float* grad
     // dW[o][i] = sum_b dZ[b][o] * X[b][i]; the longer of (out, in) takes the 128-row side of the tile
     const bool tc_dw = g_use_tc(tcx, B, l.out, l.in);     // (rows of the contraction = B, extents out x in)
     if (tc_dw) {
-        if (l.out >= l.in) tc::gemm_3xtf32(*tcx, dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, GActFn());
-        else tc::gemm_3xtf32(*tcx, X, 1, xs, dact + l.y_off, S, 1, grad + l.w_off, 1, l.in, l.in, l.out, B, nullptr, 0, 0.f, false, GActFn());
+        if (l.out >= l.in) g_tc_gemm(tcx, dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, (const float*)nullptr, 0, 0.f, false);
+        else g_tc_gemm(tcx, X, 1, xs, dact + l.y_off, S, 1, grad + l.w_off, 1, l.in, l.in, l.out, B, (const float*)nullptr, 0, 0.f, false);
     } else if (l.out >= l.in) g_gemm(dact + l.y_off, 1, S, X, xs, 1, grad + l.w_off, l.in, 1, l.out, l.in, B, nullptr, 0, 0.f, false, sm);
     else g_gemm(X, 1, xs, dact + l.y_off, S, 1, grad + l.w_off, 1, l.in, l.in, l.out, B, nullptr, 0, 0.f, false, sm);
     // dX[b][i] (+)= sum_o dZ[b][o] * W[o][i]
     if (dX) {
         if (g_use_tc(tcx, B, l.in, l.out))
-            tc::gemm_3xtf32(*tcx, dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, GActFn());
+            g_tc_gemm(tcx, dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, (const float*)nullptr, 0, 0.f, dx_accumulate);
         else g_gemm(dact + l.y_off, S, 1, th + l.w_off, l.in, 1, dX, dxs, 1, B, l.in, l.out, nullptr, 0, 0.f, dx_accumulate, sm);
     }
 }
@@ -447,7 +461,8 @@ struct GSlot {
 };
 
 // DDQN.learn / DuelingDDQN.learn on the B rows staged in slot.xs / xs2 / misc (misc = [a, r, d, pad] per row)
-static __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red, tc::Ctx* tcx = nullptr) {
+template <typename TCX = std::nullptr_t>
+static __device__ float g_td_update(const GNet& n, const GSlot& w, int B, LearnScalars& ls, float* sm, float* red, TCX tcx = nullptr) {
     const int S = n.sum_out, AD = n.ad, SDs = n.sd;
     g_net_forward(n, w.theta, w.xs, SDs, B, w.actA, sm, tcx);    // q_values = model(states)            (activations kept)
     g_q_values(n, w.actA, B, w.q, red);
@@ -599,8 +614,10 @@ static __device__ void g_init_layer(const GLayer& l, float* th, uint32_t k0, uin
     }
 }
 
-template <int SD, int AD>
-__global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunParams G) {
+// TC = false: two CTAs per SM, every dense layer on the FFMA GEMM.  TC = true: the CTA owns 128 TMEM columns and the dense
+// hidden x hidden layers run on tcgen05 (one CTA per SM: the runtime's TMEM occupancy rule).
+template <int SD, int AD, bool TC>
+__global__ void __launch_bounds__(kGThreads, TC ? 1 : 2) general_loop_kernel(const GRunParams G) {
     using RL = RowLayout<SD>;
     __shared__ __align__(16) float sm[kGSmemFloats];
     __shared__ float red[32];
@@ -610,9 +627,11 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
     __shared__ int sred[kGThreads / 32];
     __shared__ le_lane_cfg cfg_sm;
     __shared__ GNet net_sm;          // this lane's network (per-lane q_hidden / q_layers under vary_hp)
-    extern __shared__ __align__(128) unsigned char tc_smem[];   // tc::kSmemBytes: operand parts of the tensor-core GEMM
-    tc::Ctx tcs = tc::ctx_create(tc_smem);
-    tc::Ctx* const tcx = &tcs;
+    extern __shared__ __align__(128) unsigned char tc_smem[];   // TC: tc::kSmemBytes, operand parts of the tensor-core GEMM
+    tc::Ctx tcs;
+    if constexpr (TC) tcs = tc::ctx_create(tc_smem);
+    typename std::conditional<TC, tc::Ctx*, std::nullptr_t>::type tcx = nullptr;
+    if constexpr (TC) tcx = &tcs;
     const RunParams& P = G.rp;
     const GNet& n = net_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -738,12 +757,20 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
                 const u32x4 wa = philox4x32_10((uint32_t)train_steps, 0u, LE_P_ACT, 0u, k0, k1);
                 const bool explore = ((double)(wa.x >> 8) * (1.0 / 16777216.0)) < eps;
                 int action;
+                float qgap = __int_as_float(0x7fc00000);
                 if (explore) action = (int)__umulhi(wa.y, (uint32_t)AD);
                 else {
                     __syncthreads();
                     if (tid < SD) __stcg(w.xs + tid, state[tid]);   // operand rows are read with ld.global.cg: stage in the slot
                     __syncthreads();
                     action = g_greedy_row(n, w, w.xs, sm, red, ibox);
+                    if (tracing) {
+                        float q[AD];
+#pragma unroll
+                        for (int k = 0; k < AD; ++k) q[k] = w.q2[k];
+                        qgap = relative_q_gap<AD>(q, action);
+                        __syncthreads();
+                    }
                 }
                 float ns[SD], r = 0.f, d = 0.f;
                 if (c.env_kind == LE_ENV_SE) {
@@ -837,6 +864,7 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
                     const int64_t i = train_steps;
                     P.trace.action[i] = action; P.trace.explore[i] = explore ? 1 : 0;
                     P.trace.reward[i] = r; P.trace.done[i] = d; P.trace.loss[i] = loss;
+                    if (P.trace.qgap) P.trace.qgap[i] = qgap;
 #pragma unroll
                     for (int k = 0; k < SD; ++k) P.trace.next_state[i * SD + k] = ns[k];
                 }
@@ -873,19 +901,22 @@ __global__ void __launch_bounds__(kGThreads, 2) general_loop_kernel(const GRunPa
             P.out[lane_id] = o;
         }
     }
-    tc::ctx_destroy(tcs);
+    if constexpr (TC) tc::ctx_destroy(tcs);
 }
 
 // unit kernels on caller-owned canonical arrays (same layout as the slot's theta/thetaT/m/v)
-template <int SD, int AD>
-__global__ void __launch_bounds__(kGThreads, 2)
+template <int SD, int AD, bool TC>
+__global__ void __launch_bounds__(kGThreads, TC ? 1 : 2)
 general_td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, GNet n, float* th, float* thT, float* m, float* v, int32_t* tcount,
                          int q_stride, const float* __restrict__ rows, int B, float* __restrict__ loss_out, float* scratch,
                          int64_t scratch_stride) {
     __shared__ __align__(16) float sm[kGSmemFloats];
     __shared__ float red[32];
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    tc::Ctx tcs = tc::ctx_create(tc_smem);
+    tc::Ctx tcs;
+    if constexpr (TC) tcs = tc::ctx_create(tc_smem);
+    typename std::conditional<TC, tc::Ctx*, std::nullptr_t>::type tcx = nullptr;
+    if constexpr (TC) tcx = &tcs;
     const int id = blockIdx.x, tid = threadIdx.x;
     const le_lane_cfg c = *cfg_dev;
     int64_t offs[18];
@@ -913,9 +944,9 @@ general_td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, GNet n, float*
     const int t0 = tcount[id];
     ls.b1pow = pow(c.beta1, (double)t0);
     ls.b2pow = pow(c.beta2, (double)t0);
-    const float loss = g_td_update(n, w, B, ls, sm, red, &tcs);
+    const float loss = g_td_update(n, w, B, ls, sm, red, tcx);
     if (tid == 0) { loss_out[id] = loss; tcount[id] = t0 + 1; }
-    tc::ctx_destroy(tcs);
+    if constexpr (TC) tc::ctx_destroy(tcs);
 }
 
 template <int SD, int AD>

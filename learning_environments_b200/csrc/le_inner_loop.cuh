@@ -56,6 +56,16 @@ struct SmemWarp {
 
 __device__ __forceinline__ float4 ld_cg_f4(const float4* p) { return __ldcg(p); }
 
+// le_trace.qgap: (q_best - q_second) / max(|q_best|, |q_second|, 1e-12) of a greedy action choice
+template <int AD>
+__device__ __forceinline__ float relative_q_gap(const float (&q)[AD], int best) {
+    float second = -3.4e38f;
+#pragma unroll
+    for (int a = 0; a < AD; ++a)
+        if (a != best && q[a] > second) second = q[a];
+    return (q[best] - second) / fmaxf(fmaxf(fabsf(q[best]), fabsf(second)), 1e-12f);
+}
+
 // AverageMeter._mean (utils.py:103-105) over the per-lane reward list in global memory
 __device__ __forceinline__ double mean_window(const double* vals, int len, int num, int ignore_last) {
     int lo = len - num - ignore_last; if (lo < 0) lo = 0;
@@ -219,11 +229,13 @@ struct FusedLane {
                 const u32x4 wa = philox4x32_10((uint32_t)train_steps, 0u, LE_P_ACT, 0u, k0, k1);
                 const bool explore = ((double)(wa.x >> 8) * (1.0 / 16777216.0)) < eps;
                 int action;
+                float qgap = __int_as_float(0x7fc00000);
                 if (explore) action = (int)__umulhi(wa.y, (uint32_t)AD);
                 else {
                     float q[AD];
                     core.q_forward_row(state, ls.slope, q);
                     action = Core::argmax_first(q);
+                    if (tracing) qgap = relative_q_gap<AD>(q, action);
                 }
                 // ---- env.step
                 float ns[SD], r, d;
@@ -330,6 +342,7 @@ struct FusedLane {
                     const int64_t i = train_steps;
                     P.trace.action[i] = action; P.trace.explore[i] = explore ? 1 : 0;
                     P.trace.reward[i] = r; P.trace.done[i] = d; P.trace.loss[i] = loss;
+                    if (P.trace.qgap) P.trace.qgap[i] = qgap;
 #pragma unroll
                     for (int k = 0; k < SD; ++k) P.trace.next_state[i * SD + k] = ns[k];
                 }

@@ -26,6 +26,23 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _on(object):
+    """Makes the device that owns `t` current for the duration of a library call (the C ABI launches on the CURRENT device)
+    and yields that device's current stream: a GTN_Master / PopulationEvaluator built with device='cuda:1' works while
+    cuda:0 is the process's current device."""
+
+    def __init__(self, t):
+        self.dev = t.device if torch.is_tensor(t) else torch.device(t)
+        self.ctx = torch.cuda.device(self.dev)
+
+    def __enter__(self):
+        self.ctx.__enter__()
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
 def _dev(t, dtype):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), "expected a contiguous CUDA %s tensor" % dtype
     return t
@@ -171,7 +188,8 @@ class InnerLoopBuffers(object):
                               next_state=torch.zeros((trace_cap, cfg.sd), dtype=_F32, device=device),
                               reward=torch.zeros(trace_cap, dtype=_F32, device=device),
                               done=torch.zeros(trace_cap, dtype=_F32, device=device),
-                              loss=torch.full((trace_cap,), float("nan"), dtype=_F32, device=device))
+                              loss=torch.full((trace_cap,), float("nan"), dtype=_F32, device=device),
+                              qgap=torch.full((trace_cap,), float("nan"), dtype=_F32, device=device))
 
     def results(self):
         """One D2H read of the per-lane results."""
@@ -200,15 +218,16 @@ def inner_loop_run(bufs, cfgs, env_theta, env_index, keys, q_init=None, trace_la
     if bufs.trace is not None:
         tr = Trace()
         tr.cap = bufs.trace["cap"]
-        for n in ("action", "explore", "next_state", "reward", "done", "loss"):
+        for n in ("action", "explore", "next_state", "reward", "done", "loss", "qgap"):
             setattr(tr, n, bufs.trace[n].data_ptr())
     n_env = 0 if env_theta is None else env_theta.reshape(-1, max(cfg0.env_params(), 1)).shape[0]
-    check(_lib().le_inner_loop_run(
-        _ptr(bufs.cfg_dev), C.c_int(n_cfg), C.byref(cfg0), _ptr(env_theta) if env_theta is not None else None, C.c_int(n_env),
-        _ptr(env_index) if env_index is not None else None, _ptr(keys), _ptr(q_init) if q_init is not None else None,
-        _ptr(bufs.q_final) if bufs.q_final is not None else None, C.c_int(bufs.n_lanes), _ptr(bufs.out), _ptr(bufs.rewards),
-        _ptr(bufs.lengths), _ptr(bufs.test_rewards), _ptr(bufs.test_lengths), _ptr(bufs.workspace), C.c_int64(bufs.workspace.numel()),
-        C.byref(tr) if tr is not None else None, C.c_int(trace_lane), _stream()), "le_inner_loop_run")
+    with _on(bufs.workspace) as stream:
+        check(_lib().le_inner_loop_run(
+            _ptr(bufs.cfg_dev), C.c_int(n_cfg), C.byref(cfg0), _ptr(env_theta) if env_theta is not None else None, C.c_int(n_env),
+            _ptr(env_index) if env_index is not None else None, _ptr(keys), _ptr(q_init) if q_init is not None else None,
+            _ptr(bufs.q_final) if bufs.q_final is not None else None, C.c_int(bufs.n_lanes), _ptr(bufs.out), _ptr(bufs.rewards),
+            _ptr(bufs.lengths), _ptr(bufs.test_rewards), _ptr(bufs.test_lengths), _ptr(bufs.workspace), C.c_int64(bufs.workspace.numel()),
+            C.byref(tr) if tr is not None else None, C.c_int(trace_lane), stream), "le_inner_loop_run")
 
 
 def keys_tensor(keys, device):
@@ -252,30 +271,35 @@ def nes_perturb(theta, pop, member_offset, n_members, seed, generation, noise_st
     """[n_members*3, P]: rows (theta, theta+eps_i, theta-eps_i) for members member_offset.. (agents/GTN_worker.py:156-178)."""
     P = theta.numel()
     out = torch.empty((n_members * 3, P), dtype=_F32, device=theta.device)
-    check(_lib().le_nes_perturb(_ptr(_dev(theta, _F32)), C.c_int(P), C.c_int(pop), C.c_int(member_offset), C.c_int(n_members),
-                                C.c_uint32(seed), C.c_uint32(generation), C.c_float(noise_std), _ptr(out), _stream()), "le_nes_perturb")
+    with _on(theta) as stream:
+        check(_lib().le_nes_perturb(_ptr(_dev(theta, _F32)), C.c_int(P), C.c_int(pop), C.c_int(member_offset), C.c_int(n_members),
+                                    C.c_uint32(seed), C.c_uint32(generation), C.c_float(noise_std), _ptr(out), stream), "le_nes_perturb")
     return out
 
 
 def nes_noise(P, member_offset, n_members, seed, generation, noise_std, device):
     eps = torch.empty((n_members, P), dtype=_F32, device=device)
-    check(_lib().le_nes_noise(C.c_int(P), C.c_int(member_offset), C.c_int(n_members), C.c_uint32(seed), C.c_uint32(generation),
-                              C.c_float(noise_std), _ptr(eps), _stream()), "le_nes_noise")
+    with _on(eps) as stream:
+        check(_lib().le_nes_noise(C.c_int(P), C.c_int(member_offset), C.c_int(n_members), C.c_uint32(seed), C.c_uint32(generation),
+                                  C.c_float(noise_std), _ptr(eps), stream), "le_nes_noise")
     return eps
 
 
 def nes_update(theta, pop, seed, generation, noise_std, weight_decay, coef, sign):
     """update_env (agents/GTN_master.py:267-298) in place on theta; coef/sign [pop] f32 CUDA."""
-    check(_lib().le_nes_update(_ptr(_dev(theta, _F32)), C.c_int(theta.numel()), C.c_int(pop), C.c_uint32(seed), C.c_uint32(generation),
-                               C.c_float(noise_std), C.c_double(weight_decay), _ptr(_dev(coef, _F32)), _ptr(_dev(sign, _F32)), _stream()),
-          "le_nes_update")
+    assert coef.device == theta.device and sign.device == theta.device, "theta, coef and sign must live on the same GPU"
+    with _on(theta) as stream:
+        check(_lib().le_nes_update(_ptr(_dev(theta, _F32)), C.c_int(theta.numel()), C.c_int(pop), C.c_uint32(seed), C.c_uint32(generation),
+                                   C.c_float(noise_std), C.c_double(weight_decay), _ptr(_dev(coef, _F32)), _ptr(_dev(sign, _F32)), stream),
+              "le_nes_update")
 
 
 def nes_partial_update(P, member_lo, member_hi, seed, generation, noise_std, coef, sign):
     delta = torch.empty(P, dtype=_F32, device=coef.device)
-    check(_lib().le_nes_partial_update(_ptr(delta), C.c_int(P), C.c_int(member_lo), C.c_int(member_hi), C.c_uint32(seed),
-                                       C.c_uint32(generation), C.c_float(noise_std), _ptr(_dev(coef, _F32)), _ptr(_dev(sign, _F32)),
-                                       _stream()), "le_nes_partial_update")
+    with _on(coef) as stream:
+        check(_lib().le_nes_partial_update(_ptr(delta), C.c_int(P), C.c_int(member_lo), C.c_int(member_hi), C.c_uint32(seed),
+                                           C.c_uint32(generation), C.c_float(noise_std), _ptr(_dev(coef, _F32)), _ptr(_dev(sign, _F32)),
+                                           stream), "le_nes_partial_update")
     return delta
 
 

@@ -114,11 +114,12 @@ class TraceBuf(object):
         self.reward = np.zeros(cap, np.float32)
         self.done = np.zeros(cap, np.float32)
         self.loss = np.full(cap, np.nan, np.float32)
+        self.qgap = np.full(cap, np.nan, np.float32)
 
     def struct(self):
         t = Trace()
         t.cap = self.cap
-        for n in ("action", "explore", "next_state", "reward", "done", "loss"):
+        for n in ("action", "explore", "next_state", "reward", "done", "loss", "qgap"):
             setattr(t, n, getattr(self, n).ctypes.data)
         return t
 

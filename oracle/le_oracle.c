@@ -717,8 +717,14 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
             le_oracle_philox((uint32_t)L.train_steps, 0, LE_P_ACT, 0, k0, k1, w);
             double u = (double)(w[0] >> 8) * (1.0 / 16777216.0);
             int a, explore = (u < eps);
+            float qgap = NAN;
             if (explore) a = (int)mulhi32(w[1], (uint32_t)ad);
-            else { float q[LE_ORACLE_MAX_AD]; le_oracle_q_forward(c, L.th, state, q, &a); }
+            else {
+                float q[LE_ORACLE_MAX_AD]; le_oracle_q_forward(c, L.th, state, q, &a);
+                float second = -3.4e38f;
+                for (int k = 0; k < ad; ++k) if (k != a && q[k] > second) second = q[k];
+                qgap = (q[a] - second) / fmaxf(fmaxf(fabsf(q[a]), fabsf(second)), 1e-12f);   /* le_trace.qgap */
+            }
             /* env.step */
             float ns[LE_ORACLE_MAX_SD], r = 0.f, d = 0.f;
             if (c->env_kind == LE_ENV_SE) {
@@ -771,6 +777,7 @@ int le_oracle_run_lane(const le_lane_cfg* c, const float* env_theta, uint32_t k0
             if (tr && tr->cap > 0 && L.train_steps < tr->cap) {
                 int64_t i = L.train_steps;
                 tr->action[i] = a; tr->explore[i] = explore; tr->reward[i] = r; tr->done[i] = d; tr->loss[i] = loss;
+                if (tr->qgap) tr->qgap[i] = qgap;
                 memcpy(tr->next_state + i * sd, ns, sizeof(float) * sd);
             }
             L.train_steps++;

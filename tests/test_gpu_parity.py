@@ -9,7 +9,8 @@ import pytest
 import torch
 
 from oracle import c_oracle, nes, philox
-from tests.helpers import assert_params_close, cfg_from_bytes, load_golden, rel_err, sync_prefix
+from tests.helpers import (assert_divergence_is_near_tie, assert_params_close, cfg_from_bytes, first_divergence, load_golden, rel_err,
+                           sync_prefix)
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -154,6 +155,9 @@ def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
     res = bufs.results()[0]
     n_sync = sync_prefix(g["action"], tr["action"])
     assert n_sync >= min(cap, 150), "kernel left the reference trajectory after %d steps" % n_sync
+    if n_sync < min(cap, int(g["train_steps"]), int(res["train_steps"])):
+        # the kernel may leave the reference's own trajectory only at a greedy near-tie (bound derived from this lane's drift)
+        assert_divergence_is_near_tie({k: g[k] for k in ("action", "explore", "loss", "next_state", "done")}, tr, n_sync, tag)
     n = n_sync
     assert np.array_equal(tr["explore"][:n], g["explore"][:n])
     assert rel_err(tr["next_state"][:n], g["next_state"][:n], 1e-2) < 2e-4
@@ -169,6 +173,28 @@ def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
         assert np.allclose(bufs.test_rewards.cpu().numpy()[0], g["test_rewards"])
 
 
+def _assert_divergent_lanes_left_at_near_ties(ops, cfg, thetas, env_index, keys, res, oracle, limit=4):
+    """Every lane whose bookkeeping differs from the CPU restatement is re-run ALONE with a full trace on both sides (a lane's
+    result does not depend on its neighbours: test_full_size_population_is_deterministic...) and must have left the oracle at a
+    near-tie (tests/helpers.assert_divergence_is_near_tie).  Returns the number of divergent lanes."""
+    bad = np.nonzero((res["train_steps"] != oracle["train_steps"]) | (res["n_episodes"] != oracle["n_episodes"]))[0]
+    thetas = None if thetas is None else np.asarray(thetas, np.float32).reshape(-1, cfg.env_params() if cfg.env_params() else 1)
+    for i in bad[:limit]:
+        th = None if thetas is None else thetas[0 if env_index is None else int(env_index[i])]
+        cap = int(max(res["train_steps"][i], oracle["train_steps"][i]))
+        b1 = _run_fused(ops, cfg, th, [keys[i]], None, trace_cap=cap)
+        got = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in b1.trace.items()}
+        assert int(b1.results()["train_steps"][0]) == int(res["train_steps"][i])        # alone == inside the population
+        ref = c_oracle.run_lane(cfg, th, tuple(int(k) for k in keys[i]), trace_cap=cap)["trace"]
+        n = int(min(res["train_steps"][i], oracle["train_steps"][i]))
+        t = first_divergence(ref, got, n)
+        if t < n:
+            assert_divergence_is_near_tie(ref, got, t, "lane %d" % i)
+        else:   # identical steps over the common length: the difference is in the episode bookkeeping after the last step
+            assert np.allclose(np.asarray(ref.loss[:n])[~np.isnan(ref.loss[:n])], got["loss"][:n][~np.isnan(got["loss"][:n])], rtol=1e-3, atol=1e-6)
+    return len(bad)
+
+
 def test_fused_many_lanes_vs_oracle(ops):
     """64 lanes (8 SE members x 8 keys) through the lane queue; every lane vs the CPU restatement."""
     g = load_golden("trajectory_cartpole_se.npz")
@@ -182,9 +208,10 @@ def test_fused_many_lanes_vs_oracle(ops):
     bufs = _run_fused(ops, cfg, thetas, keys, None, n_env=n_env, env_index=env_index)
     res = bufs.results()
     oracle = c_oracle.run_lanes(cfg, thetas, env_index, np.array(keys, np.uint32), n_threads=8)
-    # integer bookkeeping is exact while trajectories agree; chaos (fp32 summation order) may move a few lanes
+    # integer bookkeeping is exact while trajectories agree; a lane may leave the oracle only at a greedy near-tie
     same_steps = (res["train_steps"] == oracle["train_steps"])
     assert same_steps.mean() >= 0.8, same_steps
+    _assert_divergent_lanes_left_at_near_ties(ops, cfg, thetas, env_index, keys, res, oracle)
     ok = same_steps & (res["n_episodes"] == oracle["n_episodes"])
     assert np.array_equal(res["learn_iters"][ok], oracle["learn_iters"][ok])
     assert np.allclose(res["score"][ok], oracle["score"][ok], atol=1e-9) or (np.isclose(res["score"][ok], oracle["score"][ok]).mean() > 0.8)
@@ -253,6 +280,7 @@ def test_general_kernel_many_lanes_vs_oracle(ops):
     assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0])       # pre-learning episode: exact
     same = res["train_steps"] == oracle["train_steps"]
     assert same.mean() >= 0.6, (res["train_steps"], oracle["train_steps"])
+    _assert_divergent_lanes_left_at_near_ties(ops, cfg, thetas, env_index, keys, res, oracle, limit=2)
     assert np.array_equal(res["learn_iters"][same], oracle["learn_iters"][same])
 
 
@@ -317,6 +345,7 @@ def test_fused_edge_cases_vs_oracle(ops, name, over):
     assert np.array_equal(bufs.lengths.cpu().numpy()[:, 0], oracle["lengths"][:, 0]), name       # pre-learning episode: exact
     same = (res["train_steps"] == oracle["train_steps"]) & (res["n_episodes"] == oracle["n_episodes"])
     assert same.mean() >= 0.66, (name, res["train_steps"], oracle["train_steps"])
+    _assert_divergent_lanes_left_at_near_ties(ops, cfg, theta, None, keys, res, oracle, limit=2)
     assert np.array_equal(res["learn_iters"][same], oracle["learn_iters"][same]), name
     assert np.array_equal(res["timed_out"][same], oracle["timed_out"][same]), name
     assert np.array_equal(res["test_steps"][same], oracle["test_steps"][same]) or np.isclose(res["score"][same], oracle["score"][same]).mean() >= 0.6, name
