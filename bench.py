@@ -53,9 +53,12 @@ WORKLOADS = {
     # the yaml's replay regime: rb_size 100 000 and a step budget large enough that the rings of all resident slots total > 4 GB
     # (50 200 rows x 48 B x 1776 slots): the random 48-byte gathers come from HBM, not from the 126 MB L2
     "cartpole_se_fullring": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=1184, train_episodes=500, step_budget=50000),
+    # BASELINE config 1 as the reference runs it: the yaml's population of 16 members (48 lanes on 1184+ resident warp slots):
+    # latency of ONE small generation, directly comparable with cpu_baseline.nes_generations_per_hour_pop16
+    "cartpole_se_pop16": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=16, train_episodes=10),
 }
 EXTRA_WORKLOADS = ["acrobot_se", "cartpole_rn", "cartpole_se_dueling", "acrobot_se_dueling", "acrobot_se_dueling_tc", "sweep_h1024",
-                   "cartpole_se_fullring", "vary_hp"]
+                   "cartpole_se_fullring", "cartpole_se_pop16", "vary_hp"]
 STRONG_POPULATION = 8 * 1184
 
 
@@ -620,8 +623,12 @@ def main():
                     wl[name] = compact(measure_vary_hp(D, 1, 1, 0, ffma_peak))
                 else:
                     heavy = name == "cartpole_se_fullring"
-                    r, _ = measure_nes(D, name, 1 if heavy else 2, 1, 0, 0, (), ffma_peak, with_e2e=False)
+                    small = name == "cartpole_se_pop16"
+                    r, _ = measure_nes(D, name, 1 if heavy else (5 if small else 2), 1, 0, 0, (), ffma_peak, with_e2e=small)
                     wl[name] = compact(r)
+                    if small:   # one generation of the yaml's population through the host API: wall time and lane latency
+                        wl[name]["nes_generations_per_hour"] = r["nes_generations_per_hour"]
+                        wl[name]["us_per_env_step_per_lane"] = 1e3 * r["ms_per_step"] / max(r["value"] * r["ms_per_step"] * 1e-3 / (3 * 16 * D.world), 1.0)
             except Exception as e:   # a failing side workload must not lose the headline line
                 wl[name] = {"error": "%s: %s" % (type(e).__name__, e)}
         line["workloads"] = wl

@@ -129,8 +129,8 @@ class DDQN(BaseAgent):
         self.hidden_size = int(c["hidden_size"])
         self.hidden_layer = max(int(c.get("hidden_layer", 1)), 1)
         self.feature_dim = int(c.get("feature_dim", 0)) if self._Q_KIND == Q_DUELING else 0
-        if self.hidden_layer > 2:
-            raise NotImplementedError("Q-nets with hidden_layer > 2 are outside the compiled kernel set")
+        if self.hidden_layer > 3:   # DDQN_vary / DuelingDDQN_vary sample at most yaml hidden_layer + 1 = 3 (agents/DDQN_vary.py:52-57)
+            raise NotImplementedError("Q-nets with hidden_layer > 3 are outside the compiled kernel set")
         self._act_id = ACT_IDS[str(c["activation_fn"])]
         self._env_name = config["env_name"]
         dev = _cuda_device()

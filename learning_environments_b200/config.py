@@ -37,8 +37,8 @@ def lane_cfg(config, agent_name="ddqn", env_kind=ENV_SE, use_test_env=True, fina
     c.real_env = REAL_ENV_IDS[env_name]
     if int(e.get("hidden_layer", 1)) > 1 and env_kind != ENV_REAL:
         raise NotImplementedError("SE/RN nets with hidden_layer > 1 are outside the compiled kernel set")
-    if int(a.get("hidden_layer", 1)) > 2:
-        raise NotImplementedError("Q-nets with hidden_layer > 2 are outside the compiled kernel set")
+    if int(a.get("hidden_layer", 1)) > 3:
+        raise NotImplementedError("Q-nets with hidden_layer > 3 are outside the compiled kernel set")
     if int(a.get("same_action_num", 1)) < 1:
         raise ValueError("same_action_num must be >= 1")
     c.same_action_num = int(a.get("same_action_num", 1))

@@ -482,6 +482,11 @@ def main():
         ("td_update_cartpole_dueling", lambda: gen_td_update(CP, "cartpole_dueling", 8, agent="DuelingDDQN")),
         ("td_update_acrobot_dueling", lambda: gen_td_update("default_config_acrobot.yaml", "acrobot_dueling", 9, steps=3, agent="DuelingDDQN")),
         ("td_update_cartpole_ddqn_l2", lambda: gen_td_update(CP, "cartpole_ddqn_l2", 10, steps=3, agent="DDQN", hidden_layer=2, hidden_size=150)),
+        # three hidden layers: DuelingDDQN_vary samples hidden_layer in {L-1, L, L+1} = {1, 2, 3} from default_config_acrobot.yaml
+        # (agents/DuelingDDQN_vary.py:52-57); DDQN_vary does the same around the CartPole yaml
+        ("td_update_acrobot_dueling_l3", lambda: gen_td_update("default_config_acrobot.yaml", "acrobot_dueling_l3", 47, steps=3, agent="DuelingDDQN",
+                                                               hidden_layer=3, hidden_size=96, batch_size=100)),
+        ("td_update_cartpole_ddqn_l3", lambda: gen_td_update(CP, "cartpole_ddqn_l3", 48, steps=3, agent="DDQN", hidden_layer=3, hidden_size=40)),
         ("td3_learn_cartpole", lambda: gen_td3_learn(41)),
         # soft Gumbel-softmax, relu nets, one hidden layer, policy update on every call; Acrobot shapes (sd 6, ad 3) with leakyrelu
         ("td3_learn_cartpole_soft", lambda: gen_td3_learn(43, tag="cartpole_soft", gumbel_softmax_hard=False, activation_fn="relu",
@@ -534,6 +539,9 @@ def main():
         ("trajectory_cartpole_se_ddqn_l2", lambda: gen_trajectory(CP, "cartpole_se_ddqn_l2", 23, (0x73, 0x74), "se",
                                                                   dict(train_episodes=3, test_episodes=2, init_episodes=1, hidden_layer=2,
                                                                        hidden_size=150), trace_cap=300)),
+        ("trajectory_cartpole_se_ddqn_l3", lambda: gen_trajectory(CP, "cartpole_se_ddqn_l3", 49, (0x8A, 0x8B), "se",
+                                                                  dict(train_episodes=3, test_episodes=2, init_episodes=1, hidden_layer=3,
+                                                                       hidden_size=40), trace_cap=300)),
         # hidden_layer = 0 builds the same net as 1 (models/model_utils.py:34); reward types 1 / 5 / 6 through the whole loop;
         # the real-env early-out rule (agents/base_agent.py:49-62) firing
         ("trajectory_cartpole_se_h0", lambda: gen_trajectory(CP, "cartpole_se_h0", 24, (0x75, 0x76), "se",

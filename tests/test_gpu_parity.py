@@ -71,7 +71,8 @@ def test_rn_reward_types_vs_reference_golden(ops):
             ops.rn_reward(cfg, dev(g["theta"])[None], s, s2, rr)
 
 
-@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2"])
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2",
+                                 "acrobot_dueling_l3", "cartpole_ddqn_l3"])
 def test_qnet_forward_argmax_vs_oracle(ops, tag):
     g = load_golden("td_update_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
@@ -109,7 +110,8 @@ def test_real_env_step_vs_golden(ops, tag, kind):
         assert int(el.item()) == len(g["ep%d_actions" % ep])
 
 
-@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2"])
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2",
+                                 "acrobot_dueling_l3", "cartpole_ddqn_l3"])
 def test_td_update_vs_reference_golden(ops, tag):
     g = load_golden("td_update_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
@@ -142,7 +144,7 @@ def _run_fused(ops, cfg, env_theta, keys, q_init, trace_cap=0, n_env=1, env_inde
 
 
 @pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling", "cartpole_se_k2",
-                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real", "acrobot_se_dueling", "cartpole_se_ddqn_l2",
+                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real", "acrobot_se_dueling", "cartpole_se_ddqn_l2", "cartpole_se_ddqn_l3",
                                  "cartpole_se_h0", "cartpole_rn_t1", "cartpole_rn_t5", "cartpole_rn_t6", "cartpole_real_solved"])
 def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
     """The fused persistent kernel, one lane, against the reference's own BaseAgent.train trace."""

@@ -32,9 +32,11 @@ def test_default_configs_map_to_the_reference_lane_cfg():
 
 def test_lane_cfg_rejects_shapes_outside_the_kernel_set():
     d = default_configs.get("cartpole_syn_env")
-    d["agents"]["ddqn"]["hidden_layer"] = 3
+    d["agents"]["ddqn"]["hidden_layer"] = 4          # DDQN_vary samples at most yaml hidden_layer + 1 = 3
     with pytest.raises(NotImplementedError):
         le_config.lane_cfg(d, "ddqn", ENV_SE)
+    d["agents"]["ddqn"]["hidden_layer"] = 3
+    assert le_config.lane_cfg(d, "ddqn", ENV_SE).q_layers == 3
     d["agents"]["ddqn"]["hidden_layer"] = 2          # two hidden layers: general (CTA-per-lane) kernel
     c2 = le_config.lane_cfg(d, "ddqn", ENV_SE)
     assert c2.q_layers == 2 and not c2.q_is_register_resident() and c2.q_params() == 57 * 5 + 57 * 58 + 2 * 58

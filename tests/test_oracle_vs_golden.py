@@ -40,7 +40,8 @@ def test_rn_reward_types():
             c_oracle.rn_reward(cfg, g["theta"], g["s"][0], g["s2"][0], 1.0)
 
 
-@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2"])
+@pytest.mark.parametrize("tag", ["cartpole", "acrobot", "cartpole_rn", "cartpole_dueling", "acrobot_dueling", "cartpole_ddqn_l2",
+                                 "acrobot_dueling_l3", "cartpole_ddqn_l3"])
 def test_td_update(tag):
     g = load_golden("td_update_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
@@ -77,7 +78,7 @@ def test_real_env_dynamics(tag, stepfn):
 
 
 @pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling", "cartpole_se_k2",
-                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real", "acrobot_se_dueling", "cartpole_se_ddqn_l2",
+                                 "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real", "acrobot_se_dueling", "cartpole_se_ddqn_l2", "cartpole_se_ddqn_l3",
                                  "cartpole_se_h0", "cartpole_rn_t1", "cartpole_rn_t5", "cartpole_rn_t6", "cartpole_real_solved"])
 def test_trajectory_lockstep(tag):
     g = load_golden("trajectory_%s.npz" % tag)
