@@ -231,16 +231,24 @@ static __device__ __noinline__ void g_gemm(const float* __restrict__ A, int a_si
 // Dense layer forward for M <= MT rows (greedy action M = 1, batched test rollouts M <= 16): thread j owns output
 // column j and streams its weight row W[j][:] (16-byte loads when the rows are aligned); the input rows sit in shared
 // memory as Xs[k][m] and are read as broadcasts.  Same ascending-k fmaf chain per output as g_gemm.
-template <int MT>
-__device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int M,
-                           float* __restrict__ acts, int S, float slope, float* sm) {
+// RS = 2 (layers with at most kGThreads / 2 outputs, MT >= 8): the two halves of the CTA take the two halves of the ROWS of the
+// same output column — every output keeps its ascending-k chain (bit-identical results), each thread does half the FMAs and
+// half the shared-memory reads, and all 256 threads work instead of 128.  The per-episode test() rollouts on the real env
+// (agents/base_agent.py:134-136: test_episodes greedy episodes after EVERY training episode) run through this path: it is
+// ~70 % of the warp-state samples of the Acrobot DuelingDDQN workload (profiles/r02_general_ffma.txt).
+template <int MT, int RS>
+__device__ __noinline__ void g_thin_fwd_impl(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int M,
+                                             float* __restrict__ acts, int S, float slope, float* sm) {
     constexpr int KB = (kGSmemFloats / MT) / 4 * 4 > 512 ? 512 : (kGSmemFloats / MT) / 4 * 4;
+    constexpr int MR = MT / RS;                 // rows per thread
+    constexpr int COLS = kGThreads / RS;        // output columns per pass
     const int tid = threadIdx.x;
-    for (int o0 = 0; o0 < l.out; o0 += kGThreads) {
-        const int j = o0 + tid;
-        float acc[MT];
+    const int half = tid / COLS, jt = tid % COLS, m0 = half * MR;
+    for (int o0 = 0; o0 < l.out; o0 += COLS) {
+        const int j = o0 + jt;
+        float acc[MR];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+        for (int m = 0; m < MR; ++m) acc[m] = 0.f;
         for (int k0 = 0; k0 < l.in; k0 += KB) {
             const int kn = min(KB, l.in - k0);
             __syncthreads();
@@ -249,28 +257,29 @@ __device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict
                 sm[e] = m < M ? __ldcg(X + (int64_t)m * xs + k0 + k) : 0.f;
             }
             __syncthreads();
-            if (j < l.out) {
+            if (j < l.out && m0 < M) {
                 const float* wr = th + l.w_off + (int64_t)j * l.in + k0;
                 const bool vec = ((l.in | kn) & 3) == 0 && (reinterpret_cast<uintptr_t>(wr) & 15) == 0;
                 auto mac = [&](int k, float w) {
-                    if constexpr (MT == 1) acc[0] = fmaf(sm[k], w, acc[0]);
+                    if constexpr (MR == 1) acc[0] = fmaf(sm[k * MT + m0], w, acc[0]);
                     else {
 #pragma unroll
-                        for (int m4 = 0; m4 < MT / 4; ++m4) {
-                            const float4 x = *reinterpret_cast<const float4*>(sm + k * MT + 4 * m4);
+                        for (int m4 = 0; m4 < MR / 4; ++m4) {
+                            const float4 x = *reinterpret_cast<const float4*>(sm + k * MT + m0 + 4 * m4);
                             acc[4 * m4] = fmaf(x.x, w, acc[4 * m4]); acc[4 * m4 + 1] = fmaf(x.y, w, acc[4 * m4 + 1]);
                             acc[4 * m4 + 2] = fmaf(x.z, w, acc[4 * m4 + 2]); acc[4 * m4 + 3] = fmaf(x.w, w, acc[4 * m4 + 3]);
                         }
                     }
                 };
                 if (vec) {
-#pragma unroll 8
+                    // 16 independent 16-byte weight loads in flight per thread: the stream is L2-latency bound
+#pragma unroll 16
                     for (int k = 0; k < kn; k += 4) {
                         const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wr + k));
                         mac(k, w4.x); mac(k + 1, w4.y); mac(k + 2, w4.z); mac(k + 3, w4.w);
                     }
                 } else {
-#pragma unroll 4
+#pragma unroll 8
                     for (int k = 0; k < kn; ++k) mac(k, __ldcg(wr + k));
                 }
             }
@@ -278,11 +287,20 @@ __device__ __noinline__ void g_thin_fwd(const GLayer& l, const float* __restrict
         if (j < l.out) {
             const float bj = __ldcg(th + l.b_off + j);
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-                if (m < M) __stcg(acts + (int64_t)m * S + l.y_off + j, g_act(l.act, slope, acc[m] + bj));
+            for (int m = 0; m < MR; ++m)
+                if (m0 + m < M) __stcg(acts + (int64_t)(m0 + m) * S + l.y_off + j, g_act(l.act, slope, acc[m] + bj));
         }
     }
     __syncthreads();
+}
+
+template <int MT>
+__device__ __forceinline__ void g_thin_fwd(const GLayer& l, const float* __restrict__ th, const float* __restrict__ X, int xs, int M,
+                                           float* __restrict__ acts, int S, float slope, float* sm) {
+    if constexpr (MT >= 8) {
+        if (l.out <= kGThreads / 2) { g_thin_fwd_impl<MT, 2>(l, th, X, xs, M, acts, S, slope, sm); return; }
+    }
+    g_thin_fwd_impl<MT, 1>(l, th, X, xs, M, acts, S, slope, sm);
 }
 
 // Dense layer forward with at most 4 output columns and many rows (dueling heads fd -> 1 / fd -> ad): thread b owns

@@ -17,7 +17,7 @@ from oracle import philox  # noqa: E402
 def run(agent, over, n_lanes, tc=False):
     os.environ["LE_TC"] = "1" if tc else "0"
     d = default_configs.get("cartpole_syn_env")
-    d["agents"][agent].update(train_episodes=2, test_episodes=2, init_episodes=1, batch_size=24, **over)
+    d["agents"][agent].update(dict(dict(train_episodes=2, test_episodes=2, init_episodes=1, batch_size=24), **over))
     cfg = config.lane_cfg(d, agent, ENV_SE)
     cfg.max_steps = 24
     rng = np.random.RandomState(0)
