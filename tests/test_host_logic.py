@@ -271,3 +271,44 @@ def test_vary_hp_two_ranks_gloo_matches_single_rank(tmp_path):
         assert r0[k] == single[k] and r1[k] == single[k], k
     assert len(single["rewards"]) == 2 and len(single["rewards"][0]) == 3 and len(single["rewards"][0][0]) == 2
     assert len(set(single["hidden"])) > 2          # per-lane hyper-parameters really vary
+
+
+def test_bohb_level_sweep_space_mapping_and_objective(tmp_path, monkeypatch):
+    """the reference's third optimisation level (experiments/GTNC_evaluate_cartpole_params.py:16-118) on top
+    of GTN_Master — configuration space bounds / defaults, the mapping onto the yaml config, the objective (total generations of
+    the GTN runs; a failing configuration scores +inf with the traceback recorded) and one successive-halving bracket.
+    GTN_Master runs on the oracle-backed evaluator (CPU) with tiny budgets."""
+    from learning_environments_b200 import bohb_sweep as bs
+    patch_master_for_cpu(monkeypatch)
+    monkeypatch.chdir(tmp_path)
+    ew = bs.ExperimentWrapper()
+    assert ew.get_bohb_parameters() == {"min_budget": 1, "max_budget": 3, "eta": 3, "random_fraction": 0.3, "iterations": 10000}
+    names = [s[0] for s in ew.get_configspace()]
+    assert len(names) == 18 and names[0] == "gtn_score_transform_type" and names[-1] == "cartpole_hidden_layer"
+    rng = np.random.RandomState(3)
+    for _ in range(200):           # samples respect bounds and types
+        c = bs.sample_configuration(rng)
+        for name, kind, lo, hi, log, default in bs.SPACE:
+            if kind == "cat":
+                assert c[name] in lo
+            else:
+                assert lo <= c[name] <= hi and (kind != "int" or isinstance(c[name], int))
+    d = bs.default_configuration()
+    cfg = ew.get_specific_config(d, bs.default_cartpole_config(), 1)
+    assert cfg["agents"]["ddqn"]["gamma"] == 1 - 0.01 and cfg["agents"]["ddqn"]["eps_decay"] == 1 - 0.1          # :64, :69
+    assert cfg["agents"]["gtn"]["score_transform_type"] == 7 and cfg["envs"]["CartPole-v0"]["hidden_size"] == 128
+    # tiny evaluation budget: 2 generations of 3 members, 2 training episodes per agent
+    base = bs.default_cartpole_config()
+    base["agents"]["gtn"].update(num_workers=3, max_iterations=2, quit_when_solved=False)
+    base["agents"]["ddqn"].update(train_episodes=2, test_episodes=1)
+    kw = dict(default_config=base, master_cls=gtn.GTN_Master, master_kwargs=dict(evaluator_cls=OracleEvaluator, verbose=False, seed=5))
+    ok = dict(d, ddqn_hidden_layer=1, ddqn_hidden_size=48, ddqn_batch_size=64, cartpole_hidden_size=48, ddqn_init_episodes=1)
+    r = ew.compute(str(tmp_path), 0, 0, ok, budget=3, **kw)
+    assert r["loss"] == 3 * 2 and r["info"]["error"] == ""                # three GTN runs x max_iterations generations (:91-95)
+    bad = dict(ok, cartpole_hidden_layer=2)                               # SE with two hidden layers: outside the kernel set
+    r = ew.compute(str(tmp_path), 0, 1, bad, budget=1, **kw)
+    assert r["loss"] == float("inf") and "NotImplementedError" in r["info"]["error"]
+    res = bs.run_sweep(n_configs=3, seed=1, working_dir=str(tmp_path), default_config=base, master_cls=gtn.GTN_Master,
+                       master_kwargs=kw["master_kwargs"])
+    assert res[0]["budget"] >= res[-1]["budget"] and len(res) >= 3
+    assert all(np.isfinite(x["loss"]) or x["info"]["error"] for x in res)
