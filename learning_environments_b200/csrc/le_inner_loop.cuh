@@ -48,7 +48,7 @@ struct SmemWarp {
     static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
     static constexpr int CFG_F = (sizeof(le_lane_cfg) + 15) / 16 * 4;
     static constexpr int RED_R = (U <= 2 ? LE_R_U2 : 4);
-    static constexpr int RED_F = ((LE_PIPELINED || LE_DQ_SHFL) ? 2 : 1) * (RED_R * (((AD + 1) / 2 + AD + 1) / 2) * 32 * 4 + RED_R * 4);  // LaneCore::RED_F + DQS_F
+    static constexpr int RED_F = LaneCore<SD, AD, U, QACT_TANH>::SMEM_RED_F;   // reduction buffers, or the row-owner region
     static constexpr int FLOATS = BUF_F + MV_F + CFG_F + RED_F;
     static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F, OFF_RED = BUF_F + MV_F + CFG_F;
     static_assert(FLOATS % 4 == 0 && OFF_RED % 4 == 0 && STAGE_ONE_F % 4 == 0, "float4 accesses of the stage / reduction buffer need 16-byte alignment");
@@ -203,6 +203,8 @@ struct FusedLane {
         if (P.q_init) core.load_net(P.q_init + (int64_t)lane_id * P.q_stride, H, lane, 0);
         else core.init_online(H, lane, k0, k1);
         core.copy_online_to_target();  // model_target.load_state_dict(model.state_dict())   agents/DDQN.py:36
+        Core::init_row_region(smem + SW::OFF_RED, lane);
+        core.publish_weights(smem + SW::OFF_RED, lane);
         Core::zero_moments(mv, lane);
         LearnScalars ls;
         fill_learn_scalars(ls, c);
@@ -336,6 +338,7 @@ struct FusedLane {
                     }
                     loss = warp_allreduce_sum(loss_part) / (float)B;
                     core.adam_polyak(ls, mv, lane);
+                    core.publish_weights(smem + SW::OFF_RED, lane);
                     learn_iters += 1;
                 }
                 if (tracing && train_steps < P.trace.cap && lane == 0) {

@@ -114,6 +114,8 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
     const int64_t o = (int64_t)id * q_stride;
     core.load_net(th + o, H, lane, 0);
     core.load_net(thT + o, H, lane, 1);
+    Core::init_row_region(smem + SW::OFF_RED, lane);
+    core.publish_weights(smem + SW::OFF_RED, lane);
     Core::load_moments(mv, m + o, v + o, H, lane);
     LearnScalars ls;
     fill_learn_scalars(ls, c);
