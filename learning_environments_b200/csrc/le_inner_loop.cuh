@@ -200,6 +200,7 @@ struct FusedLane {
         const bool tracing = P.trace.cap > 0 && lane_id == P.trace_lane;
 
         Core core;
+        core.bind(smem + SW::OFF_RED, lane);
         if (P.q_init) core.load_net(P.q_init + (int64_t)lane_id * P.q_stride, H, lane, 0);
         else core.init_online(H, lane, k0, k1);
         core.copy_online_to_target();  // model_target.load_state_dict(model.state_dict())   agents/DDQN.py:36

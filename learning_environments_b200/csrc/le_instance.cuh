@@ -80,8 +80,12 @@ __global__ void qnet_forward_kernel(const float* __restrict__ q_theta, int q_str
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
+    // row-owner cores keep their weights in shared-memory records (4 warps per block, launch_qnet_forward)
+    __shared__ float wrec[4][Core::kRow ? Core::ROW_WREC_F : 1];
     Core core;
+    core.bind(wrec[(threadIdx.x >> 5) & 3], lane);
     core.load_net(q_theta + (int64_t)row * q_stride, H, lane, 0);
+    core.publish_weights(nullptr, lane);
     float s[SD], q[AD];
 #pragma unroll
     for (int i = 0; i < SD; ++i) s[i] = state[(int64_t)row * SD + i];
@@ -111,6 +115,7 @@ td_update_kernel(const le_lane_cfg* __restrict__ cfg_dev, float* th, float* thT,
     const le_lane_cfg c = *cfg_dev;
     const int H = c.q_hidden;
     Core core;
+    core.bind(smem + SW::OFF_RED, lane);
     const int64_t o = (int64_t)id * q_stride;
     core.load_net(th + o, H, lane, 0);
     core.load_net(thT + o, H, lane, 1);
