@@ -1,6 +1,7 @@
 // le_api.cu — the C ABI of include/le_b200.h: argument checking, kernel-set dispatch, NES kernels.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -262,8 +263,21 @@ struct Plan {
     GeneralPlan gp;
     const InstanceOps* ops;
     int grid, slots, ring_cap;
+    bool mw;   // multi-warp lanes: one lane per CTA
     int64_t ring_stride_f, pack_stride_f, pack_bytes, rings_bytes, total_bytes, off_rings, off_counter;
 };
+
+// Multi-warp lanes (inner_loop_mw_kernel) for small populations: a lane gets a whole CTA instead of one warp (2.7x shorter
+// generations at the yaml's population of 16, profiles/r02_mw_lanes.txt); up to two lanes per SM queue on the CTAs before the
+// warp-per-lane kernel, which runs every lane at once, is the faster choice.
+// LE_MW=0 never, LE_MW=1 whenever the kernel set has the kernel (any lane count), default: auto.
+static bool use_mw_lanes(const InstanceOps* ops, int n_lanes, int sms) {
+    if (ops->mw_warps <= 1) return false;
+    const char* e = getenv("LE_MW");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return n_lanes <= 2 * sms;
+}
 
 static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
     { const int rc0 = check_env_cfg(c); if (rc0 != LE_OK) return rc0; }
@@ -273,6 +287,7 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
         return LE_EINVAL;
     }
     pl->general = !is_register_resident(c);
+    pl->mw = false;
     if (c->q_layers > 3) { le_set_error("Q-network hidden_layer=%d: the compiled kernel set covers up to 3 hidden layers", c->q_layers); return LE_EUNSUPPORTED; }
     // the env-packing / unit kernels of any kernel set with the right (sd, ad) serve the general path too
     const InstanceOps* ops = pl->general ? le_find_instance(c->sd, c->ad, 1, QACT_TANH) : instance_for(c, c->q_hidden);
@@ -292,6 +307,11 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
         pl->grid = pl->gp.grid;
         pl->slots = pl->grid;
         pl->ring_stride_f = pl->gp.slot_floats;   // one slot = ring + parameters + activations
+    } else if (use_mw_lanes(ops, n_lanes, sms)) {
+        pl->mw = true;
+        pl->grid = n_lanes < sms ? n_lanes : sms;
+        pl->slots = pl->grid;
+        pl->ring_stride_f = (int64_t)pl->ring_cap * ops->ring_row_floats();
     } else {
         int per_sm = ops->inner_max_ctas_per_sm();
         if (per_sm < 1) per_sm = 1;
@@ -520,6 +540,7 @@ int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* 
     P.work_counter = counter;
     if (trace_host && trace_host->cap > 0) { P.trace = *trace_host; P.trace_lane = trace_lane; }
     if (pl.general) LE_CUDA_CHECK(general_launch(c, P, P.rings, pl.gp, st));
+    else if (pl.mw) LE_CUDA_CHECK(pl.ops->launch_inner_mw(P, pl.grid, st));
     else LE_CUDA_CHECK(pl.ops->launch_inner(P, pl.grid, st));
     return LE_OK;
 }

@@ -37,7 +37,7 @@ template <int U> constexpr int inner_warps() { return U <= 2 ? kWarpsPerCta : LE
 
 
 // Per-warp shared memory: [stage rows | test-phase weight image (aliased)] [Adam m, v] [lane configuration] [reduction]
-template <int SD, int AD, int U>
+template <int SD, int AD, int U, int ROW = -1>
 struct SmemWarp {
     using SL = StageLayout<SD>;
     static constexpr int PUP = SD + 1 + AD;           // per-unit record of the test-phase weight image (scalar reads, broadcast)
@@ -48,7 +48,7 @@ struct SmemWarp {
     static constexpr int MV_F = 2 * (U * (SD + 1 + AD) + AD) * 32;
     static constexpr int CFG_F = (sizeof(le_lane_cfg) + 15) / 16 * 4;
     static constexpr int RED_R = (U <= 2 ? LE_R_U2 : 4);
-    static constexpr int RED_F = LaneCore<SD, AD, U, QACT_TANH>::SMEM_RED_F;   // reduction buffers, or the row-owner region
+    static constexpr int RED_F = LaneCore<SD, AD, U, QACT_TANH, ROW>::SMEM_RED_F;   // reduction buffers, or the row-owner region
     static constexpr int FLOATS = BUF_F + MV_F + CFG_F + RED_F;
     static constexpr int OFF_MV = BUF_F, OFF_CFG = BUF_F + MV_F, OFF_RED = BUF_F + MV_F + CFG_F;
     static_assert(FLOATS % 4 == 0 && OFF_RED % 4 == 0 && STAGE_ONE_F % 4 == 0, "float4 accesses of the stage / reduction buffer need 16-byte alignment");
@@ -91,11 +91,108 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int SD, int AD, int U, int ACT>
+// Multi-warp lanes (W > 1, inner_loop_mw_kernel): shared state of one CTA = one lane.  The leader warp (warp 0) runs the lane's
+// control flow; for every DDQN.learn it publishes a command and the W warps split the minibatch into 32-row passes.
+struct MwShared {
+    int cmd;                 // 0: exit, 1: learn, 2: new lane (configuration is in the leader's shared memory)
+    int lane_id, rb_size, pad;
+    long long learn_iters;
+    float b2[4], tb2[4];     // output biases of the online / target net (registers of the leader)
+};
+template <int W>
+__device__ __forceinline__ void mw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(W * 32) : "memory"); }
+template <int U> constexpr int mw_warps() { return U <= 2 ? 8 : (U <= 4 ? 6 : 4); }
+
+template <int SD, int AD, int U, int ACT, int W = 1>
 struct FusedLane {
-    using Core = LaneCore<SD, AD, U, ACT>;
+    using Core = LaneCore<SD, AD, U, ACT, (W > 1 ? 1 : -1)>;
     using RL = RowLayout<SD>;
-    using SW = SmemWarp<SD, AD, U>;
+    using SW = SmemWarp<SD, AD, U, (W > 1 ? 1 : -1)>;
+    using SL0 = StageLayout<SD>;
+    // multi-warp lanes: per-worker shared memory = a 32-row stage + the row-owner scratch; exchange = gradients, bias gradients, loss
+    static constexpr int MW_STAGE_F = 32 * SL0::STAGE_F;
+    static constexpr int MW_WORKER_F = MW_STAGE_F + Core::ROW_SCRATCH_F;
+    static constexpr int MW_NEX = U * (SD + 1 + AD) + AD + 1;
+    static constexpr int MW_EX_F = (W - 1) * MW_NEX * 32;
+    static constexpr int MW_SH_F = (sizeof(MwShared) + 15) / 16 * 4;
+    static constexpr int MW_CTA_F = SW::FLOATS + (W - 1) * MW_WORKER_F + MW_EX_F + MW_SH_F;
+
+    // This warp's share of one DDQN.learn: passes w, w + W, ... of 32 sampled rows each (same Philox blocks as the single-warp
+    // gather: block = row / 4 of the minibatch).  Gradients accumulate in core.a*, returns the warp's share of sum(delta^2).
+    static __device__ __forceinline__ float mw_td_share(Core& core, int w, const float* wrec, float* stage, float* scratch, const float* ring,
+                                                        int rb_size, long long learn_iters, uint32_t k0, uint32_t k1, const LearnScalars& ls, int lane) {
+        core.zero_grads();
+        float loss_part = 0.f;
+        const int B = ls.batch;
+        const int npass = (B + 31) >> 5;
+        const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
+        for (int p = w; p < npass; p += W) {
+            const int nrows = min(32, B - 32 * p);
+            if (lane < 8) {
+                const u32x4 wv = philox4x32_10((uint32_t)learn_iters, (uint32_t)(8 * p + lane), LE_P_SAMPLE, 0u, k0, k1);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int rr = 4 * lane + kk;
+                    if (rr < nrows) {
+                        const uint32_t idx = __umulhi(pick(wv, kk), (uint32_t)rb_size);
+                        const float* src = ring + (int64_t)idx * RL::ROWF;
+#pragma unroll
+                        for (int q = 0; q < RL::ROW_VEC; ++q) cp_async16(stage_sa + (uint32_t)((rr * SL0::STAGE_F + 4 * q) * 4), src + 4 * q);
+                    } else {
+                        float4* z = reinterpret_cast<float4*>(stage + rr * SL0::STAGE_F);
+#pragma unroll
+                        for (int q = 0; q < RL::ROW_VEC; ++q) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
+            loss_part += core.td_rows_rowown(stage, wrec, scratch, nrows, ls, lane);
+            __syncwarp();
+        }
+        return loss_part;
+    }
+    // worker warps of a multi-warp lane
+    static __device__ void mw_worker(const RunParams& P, int slot, int w, float* lead_smem, float* my_smem, MwShared* sh, float* ex, int lane) {
+        Core core;
+        core.bind(lead_smem + SW::OFF_RED, lane);
+        float* stage = my_smem;
+        float* scratch = my_smem + MW_STAGE_F;
+        Core::init_row_scratch(scratch, lane);
+        const float* ring = P.rings + (int64_t)slot * P.ring_stride;
+        const le_lane_cfg& c = *reinterpret_cast<const le_lane_cfg*>(lead_smem + SW::OFF_CFG);
+        LearnScalars ls;
+        uint32_t k0 = 0, k1 = 0;
+        for (;;) {
+            mw_bar<W>(1);
+            const int cmd = sh->cmd;
+            if (cmd == 0) break;
+            if (cmd == 2) {
+                fill_learn_scalars(ls, c);
+                k0 = P.keys[2 * sh->lane_id]; k1 = P.keys[2 * sh->lane_id + 1];
+            } else {
+#pragma unroll
+                for (int a = 0; a < AD; ++a) { core.b2[a] = sh->b2[a]; core.tb2[a] = sh->tb2[a]; }
+                core.publish_weights(nullptr, lane);
+                const float lp = mw_td_share(core, w, lead_smem + SW::OFF_RED, stage, scratch, ring, sh->rb_size, sh->learn_iters, k0, k1, ls, lane);
+                float* e = ex + (w - 1) * MW_NEX * 32 + lane;
+                int k = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int i = 0; i < SD; ++i) e[32 * (k++)] = core.g_w1(u, i);
+                    e[32 * (k++)] = core.g_b1(u);
+#pragma unroll
+                    for (int a = 0; a < AD; ++a) e[32 * (k++)] = core.g_w2(u, a);
+                }
+#pragma unroll
+                for (int a = 0; a < AD; ++a) e[32 * (k++)] = core.gb2[a];
+                e[32 * k] = lp;
+            }
+            mw_bar<W>(2);
+        }
+    }
 
     // BaseAgent.test: greedy rollouts on the real env, one episode per thread, weights broadcast from smem.
     static __device__ __forceinline__ double run_test(const Core& core, float* smem, const le_lane_cfg& c, float slope,
@@ -178,7 +275,7 @@ struct FusedLane {
         return sum / (double)c.test_episodes;  // statistics.mean
     }
 
-    static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane) {
+    static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane, MwShared* sh = nullptr, float* ex = nullptr) {
         using SL = StageLayout<SD>;
         float* mv = smem + SW::OFF_MV;
         {   // lane configuration -> shared memory (read on demand instead of pinning ~46 registers)
@@ -209,6 +306,11 @@ struct FusedLane {
         Core::zero_moments(mv, lane);
         LearnScalars ls;
         fill_learn_scalars(ls, c);
+        if constexpr (W > 1) {   // workers pick up the lane's configuration and keys
+            if (lane == 0) { sh->cmd = 2; sh->lane_id = lane_id; }
+            mw_bar<W>(1);
+            mw_bar<W>(2);
+        }
 
         int rb_ptr = 0, rb_size = 0;
         int64_t train_steps = 0, learn_iters = 0, test_steps = 0;
@@ -296,10 +398,35 @@ struct FusedLane {
                 // ---- learn (agents/DDQN.py:60-95)
                 float loss = __int_as_float(0x7fc00000);
                 if (episode >= c.init_episodes) {
-                    __syncwarp();  // the appended row is visible to the whole warp
-                    core.zero_grads();
                     float loss_part = 0.f;
                     const int B = ls.batch;
+                    if constexpr (W > 1) {
+                        if (lane == 0) {
+                            sh->cmd = 1; sh->rb_size = rb_size; sh->learn_iters = learn_iters;
+#pragma unroll
+                            for (int a = 0; a < AD; ++a) { sh->b2[a] = core.b2[a]; sh->tb2[a] = core.tb2[a]; }
+                        }
+                        mw_bar<W>(1);     // the appended row, the weights and the command are visible to every warp of the lane
+                        loss_part = mw_td_share(core, 0, smem + SW::OFF_RED, smem, smem + SW::OFF_RED + Core::ROW_WREC_F, ring, rb_size, learn_iters, k0, k1, ls, lane);
+                        mw_bar<W>(2);     // every warp's gradients are in the exchange buffer: add them in warp order
+                        for (int w = 1; w < W; ++w) {
+                            const float* e = ex + (w - 1) * MW_NEX * 32 + lane;
+                            int k = 0;
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                                for (int i = 0; i < SD; ++i) core.a1[u][i].x += e[32 * (k++)];
+                                core.ab1[u].x += e[32 * (k++)];
+#pragma unroll
+                                for (int a = 0; a < AD; ++a) core.a2[u][a].x += e[32 * (k++)];
+                            }
+#pragma unroll
+                            for (int a = 0; a < AD; ++a) core.gb2[a] += e[32 * (k++)];
+                            loss_part += e[32 * k];
+                        }
+                    } else {
+                    __syncwarp();  // the appended row is visible to the whole warp
+                    core.zero_grads();
                     // replay_buffer.sample: idx = randint(0, size, B) on the P_SAMPLE stream (utils.py:35).  Thread t < 16
                     // gathers the 4 rows of Philox block (round*16 + t) with 16-byte cp.async (global -> shared, no
                     // registers); round k+1 is in flight while round k is computed.
@@ -336,6 +463,7 @@ struct FusedLane {
                         __syncwarp();
                         loss_part += core.td_rows(smem + (sc & 1) * SW::STAGE_ONE_F, smem + SW::OFF_RED, nrows, ls, lane);
                         __syncwarp();
+                    }
                     }
                     loss = warp_allreduce_sum(loss_part) / (float)B;
                     core.adam_polyak(ls, mv, lane);
@@ -408,6 +536,38 @@ __global__ void __launch_bounds__(inner_warps<U>() * 32, (U <= 2 ? LE_MIN_CTAS_U
         if (lane_id >= P.n_lanes) break;
         FusedLane<SD, AD, U, ACT>::run(P, lane_id, slot, smem, lane);
         __syncwarp();
+    }
+}
+
+// Multi-warp lanes: ONE lane per CTA of mw_warps<U>() warps (small populations: fewer lanes than SMs).  Warp 0 runs the lane
+// (FusedLane<..., W>::run); the minibatch of every DDQN.learn is split into 32-row passes over all warps (row-owner TD update on
+// the lane's shared weight records), the gradients meet in shared memory and warp 0 takes the Adam / Polyak step.
+template <int SD, int AD, int U, int ACT>
+__global__ void __launch_bounds__(mw_warps<U>() * 32, 1) inner_loop_mw_kernel(const RunParams P) {
+    constexpr int W = mw_warps<U>();
+    using FL = FusedLane<SD, AD, U, ACT, W>;
+    extern __shared__ __align__(16) float smem_dyn[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x;
+    float* ex = smem_dyn + FL::SW::FLOATS + (W - 1) * FL::MW_WORKER_F;
+    MwShared* sh = reinterpret_cast<MwShared*>(ex + FL::MW_EX_F);
+    if (warp == 0) {
+        bool first = true;
+        for (;;) {
+            int lane_id = slot;
+            if (!first) {
+                if (lane == 0) lane_id = (int)gridDim.x + atomicAdd(P.work_counter, 1);
+                lane_id = __shfl_sync(LE_FULL_MASK, lane_id, 0);
+            }
+            first = false;
+            if (lane_id >= P.n_lanes) break;
+            FL::run(P, lane_id, slot, smem_dyn, lane, sh, ex);
+            __syncwarp();
+        }
+        if (lane == 0) sh->cmd = 0;
+        mw_bar<W>(1);
+    } else {
+        FL::mw_worker(P, slot, warp, smem_dyn, smem_dyn + FL::SW::FLOATS + (warp - 1) * FL::MW_WORKER_F, sh, ex, lane);
     }
 }
 

@@ -9,6 +9,8 @@ namespace le {
 struct InstanceOps {
     int sd, ad, units, act;  // act: QACT_TANH / QACT_LEAKY
     int inner_warps;         // warps (= lane slots) per CTA of the fused kernel
+    int mw_warps;            // warps per lane of the multi-warp (one lane per CTA) kernel; 0 if its shared memory does not fit
+    cudaError_t (*launch_inner_mw)(const RunParams& P, int grid, cudaStream_t st);
     // fused persistent kernel
     int (*inner_max_ctas_per_sm)();
     cudaError_t (*launch_inner)(const RunParams& P, int grid, cudaStream_t st);
@@ -180,6 +182,17 @@ struct InstanceImpl {
         inner_loop_kernel<SD, AD, U, ACT><<<grid, kInnerWarps * 32, kInnerSmemBytes, st>>>(P);
         return cudaGetLastError();
     }
+    using MwLane = FusedLane<SD, AD, U, ACT, mw_warps<U>()>;
+    static constexpr size_t kMwSmemBytes = (size_t)MwLane::MW_CTA_F * sizeof(float);
+    static constexpr bool kMwOk = kMwSmemBytes <= 227 * 1024;
+    static cudaError_t launch_inner_mw(const RunParams& P, int grid, cudaStream_t st) {
+        if constexpr (kMwOk) {
+            cudaError_t e = cudaFuncSetAttribute(inner_loop_mw_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMwSmemBytes);
+            if (e != cudaSuccess) return e;
+            inner_loop_mw_kernel<SD, AD, U, ACT><<<grid, mw_warps<U>() * 32, kMwSmemBytes, st>>>(P);
+            return cudaGetLastError();
+        } else return cudaErrorInvalidConfiguration;
+    }
     static int64_t ring_row_floats() { return RowLayout<SD>::ROWF; }
     static int64_t se_pack_vec4(int H) { return SePack<SD, AD>::pack_vec4(H); }
     static int64_t rn_pack_vec4(int H) { return RnPack<SD>::pack_vec4(H); }
@@ -226,7 +239,7 @@ struct InstanceImpl {
         return cudaGetLastError();
     }
     static const InstanceOps* ops() {
-        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
+        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, kMwOk ? mw_warps<U>() : 0, launch_inner_mw, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
                                       rn_pack_vec4, launch_pack_se, launch_pack_rn, launch_se_forward, launch_rn_reward,
                                       launch_qnet_forward, launch_td_update};
         return &o;

@@ -146,8 +146,12 @@ def _run_fused(ops, cfg, env_theta, keys, q_init, trace_cap=0, n_env=1, env_inde
 @pytest.mark.parametrize("tag", ["cartpole_se", "acrobot_se", "cartpole_rn", "cartpole_se_notest", "cartpole_se_dueling", "cartpole_se_k2",
                                  "cartpole_rn_k3", "cartpole_real_k2", "acrobot_real", "acrobot_se_dueling", "cartpole_se_ddqn_l2", "cartpole_se_ddqn_l3",
                                  "cartpole_se_h0", "cartpole_rn_t1", "cartpole_rn_t5", "cartpole_rn_t6", "cartpole_real_solved"])
-def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
-    """The fused persistent kernel, one lane, against the reference's own BaseAgent.train trace."""
+@pytest.mark.parametrize("mw", ["0", "1"])
+def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag, mw, monkeypatch):
+    """The fused persistent kernel, one lane, against the reference's own BaseAgent.train trace — on the warp-per-lane kernel
+    (LE_MW=0) and on the multi-warp lane kernel a single lane would get by default (LE_MW=1; same kernel for the lanes of the
+    general CTA-per-lane family, which has no multi-warp variant)."""
+    monkeypatch.setenv("LE_MW", mw)
     g = load_golden("trajectory_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
     key = [tuple(int(k) for k in g["key"])]
@@ -173,6 +177,37 @@ def test_fused_trajectory_lockstep_vs_reference_golden(ops, tag):
         assert np.array_equal(bufs.lengths.cpu().numpy()[0, :len(g["lengths"])], g["lengths"])
         assert np.allclose(bufs.rewards.cpu().numpy()[0, :len(g["rewards"])], g["rewards"], rtol=1e-4, atol=1e-4)
         assert np.allclose(bufs.test_rewards.cpu().numpy()[0], g["test_rewards"])
+
+
+def test_multi_warp_lanes_deterministic_and_independent_of_scheduling(ops, monkeypatch):
+    """Multi-warp lanes (one lane per CTA, the minibatch of every learn() split over the CTA's warps; selected when there are
+    fewer lanes than SMs, forced here with LE_MW=1 so that 200 lanes queue on the CTAs): bit-identical across launches and
+    independent of the lane queue; against the warp-per-lane kernel the integer bookkeeping of lanes that stay off near-ties
+    agrees and the final Q-nets agree to fp32 reassociation."""
+    g = load_golden("trajectory_cartpole_se.npz")
+    cfg = cfg_from_bytes(g["cfg"])
+    cfg.train_episodes, cfg.test_episodes, cfg.init_episodes = 4, 5, 1
+    n_env, n = 4, 200
+    rng = np.random.RandomState(11)
+    thetas = (g["env_theta"][None] + rng.standard_normal((n_env, g["env_theta"].size)).astype(np.float32) * 0.02).astype(np.float32)
+    keys = [philox.lane_key(41, 1, i, i % 3, 0) for i in range(n)]
+    env_index = (np.arange(n) % n_env).astype(np.int32)
+    monkeypatch.setenv("LE_MW", "1")
+    r1, rew1, q1 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
+    r2, rew2, q2 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
+    sub = rng.permutation(n)[:37]
+    r3, rew3, q3 = _full_size_run(ops, cfg, thetas, [keys[i] for i in sub], env_index[sub], n_env)
+    for f in ("n_episodes", "train_steps", "learn_iters", "test_steps", "score"):
+        assert np.array_equal(r1[f], r2[f]), f
+        assert np.array_equal(r3[f], r1[f][sub]), f
+    assert np.array_equal(rew1, rew2) and np.array_equal(q1, q2)
+    assert np.array_equal(rew3, rew1[sub]) and np.array_equal(q3, q1[sub])
+    monkeypatch.setenv("LE_MW", "0")
+    r0, rew0, q0 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
+    same = (r0["train_steps"] == r1["train_steps"]) & (r0["n_episodes"] == r1["n_episodes"])
+    assert same.mean() >= 0.8, same
+    assert np.array_equal(r0["learn_iters"][same], r1["learn_iters"][same])
+    assert rel_err(q1[same], q0[same]) < 5e-2      # four episodes of training amplify the last-bit differences of the gradient sums
 
 
 def _assert_divergent_lanes_left_at_near_ties(ops, cfg, thetas, env_index, keys, res, oracle, limit=4):
@@ -386,11 +421,15 @@ def _full_size_run(ops, cfg, theta, keys, env_index=None, n_env=1):
 
 
 @pytest.mark.parametrize("tag", ["cartpole_se", "cartpole_se_dueling"])
-def test_full_size_population_is_deterministic_and_independent_of_scheduling(ops, tag):
+def test_full_size_population_is_deterministic_and_independent_of_scheduling(ops, tag, monkeypatch):
     """bench.py's lane count (one full residency wave + a ragged second one) at the yaml batch size.  (1) the same launch
     twice is bit-identical; (2) a lane's result does not depend on which slot runs it, how many lanes share the GPU or
     the order of the lane queue (run a permuted subset alone); (3) every lane made progress and the bookkeeping is
-    consistent (learn_iters = steps after the init episodes, episode lengths sum to train_steps)."""
+    consistent (learn_iters = steps after the init episodes, episode lengths sum to train_steps).
+    LE_MW=0 keeps the 53-lane subset on the warp-per-lane kernel of the full population (fewer lanes than SMs would otherwise
+    select the multi-warp lanes, whose gradient summation order differs in the last bit); the multi-warp family has its own
+    run of the same property below."""
+    monkeypatch.setenv("LE_MW", "0")
     g = load_golden("trajectory_%s.npz" % tag)
     cfg = cfg_from_bytes(g["cfg"])
     dueling = tag.endswith("dueling")
