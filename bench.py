@@ -57,6 +57,8 @@ WORKLOADS = {
     # latency of ONE small generation, directly comparable with cpu_baseline.nes_generations_per_hour_pop16
     "cartpole_se_pop16": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=16, train_episodes=10),
 }
+# (f)2: TD3_discrete_vary lanes (le_td3.cu, CTA-per-lane) on the CartPole SE with the yaml's td3_discrete_vary section; host-buffer entry
+TD3_WORKLOAD = dict(cfg="cartpole_syn_env", lanes_per_gpu=592, train_episodes=3, init_episodes=1)
 EXTRA_WORKLOADS = ["acrobot_se", "cartpole_rn", "cartpole_se_dueling", "acrobot_se_dueling", "acrobot_se_dueling_tc", "sweep_h1024",
                    "cartpole_se_fullring", "cartpole_se_pop16", "vary_hp"]
 STRONG_POPULATION = 8 * 1184
@@ -427,6 +429,74 @@ def measure_vary_hp(D, steps, warmup, members_per_gpu=0, ffma_peak=None):
     }
 
 
+def measure_td3(D, steps, warmup, lanes_per_gpu=0, ffma_peak=None):
+    """TD3_discrete_vary lanes through le_td3_run_host (HOST buffers in and out: the timed region holds the H2D of the SE / initial
+    nets / keys, the persistent kernel and the D2H of the lane results), wall clock around the call, max over ranks."""
+    import copy
+    import torch
+    from learning_environments_b200 import agents as A, default_configs, ops
+    from learning_environments_b200.envs import EnvFactory
+    from learning_environments_b200.rng import lane_keys
+    w = TD3_WORKLOAD
+    d = copy.deepcopy(default_configs.get(w["cfg"]))
+    a = d["agents"]["td3_discrete_vary"]
+    w = dict(w, train_episodes=int(os.environ.get("LE_TD3_TRAIN_EPISODES", w["train_episodes"])))   # profiling aid (ncu replays the kernel)
+    a.update(vary_hp=False, train_episodes=w["train_episodes"], init_episodes=w["init_episodes"])
+    n = lanes_per_gpu or w["lanes_per_gpu"]
+    torch.manual_seed(7)
+    fac = EnvFactory(d)
+    env, real = fac.generate_virtual_env(), fac.generate_real_env()
+    agent = A.TD3_discrete_vary(env=real, min_action=real.get_min_action(), max_action=real.get_max_action(), config=d)
+    env.set_agent_params(same_action_num=agent.same_action_num, gamma=agent.gamma)
+    t, theta, nets = agent._td3_cfg(env, real, w["train_episodes"], True, 1e9)
+    pa, pc = ops.td3_param_counts(t)
+    sd, ad, H, L, B = t.base.sd, t.base.ad, t.base.q_hidden, max(t.base.q_layers, 1), t.base.batch_size
+    f_a = 2 * (sd * H + (L - 1) * H * H + H * ad)
+    f_c = 2 * ((sd + ad) * H + (L - 1) * H * H + H)
+    f_env = 2 * (3 * t.base.env_hidden * (sd + ad) + t.base.env_hidden * (sd + 2))
+    f_learn = B * (f_a + 8 * f_c + (3 * f_a + 2 * f_c) / max(t.policy_delay, 1))
+    nets_n = [np.repeat(x[None], 1, 0) for x in nets]
+
+    def step(g):
+        keys = lane_keys(977, g, D.rank * n + np.arange(n), np.zeros(n, int), np.zeros(n, int))
+        return ops.td3_run_host(t, theta, None, keys, nets_n[0], nets_n[1], nets_n[2], device=torch.cuda.current_device())
+
+    for g in range(warmup):
+        step(g)
+    D.barrier()
+    sampler = ClockSampler(D.local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    steps_done, learns = 0, 0
+    for k in range(steps):
+        res = step(warmup + k)
+        steps_done += int(res["out"]["train_steps"].sum())
+        learns += int(res["out"]["learn_iters"].sum())
+    D.barrier()
+    sec = time.perf_counter() - t0
+    clocks = sampler.stop()
+    mx, sm = D.max_sum([sec, float(steps_done), float(learns)])
+    sec, steps_all, learns_all = mx[0], sm[1], sm[2]
+    achieved = (steps_all * (f_env + f_a) + learns_all * f_learn) / D.world / sec / 1e12
+    ffma_peak = ffma_peak or ops.bench_ffma()
+    val = steps_all / sec
+    return {
+        "metric": "se_env_steps_per_s", "value": val, "unit": "env-steps/s", "n_gpus": D.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * sec / max(steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "td3_discrete: %d TD3_discrete_vary lanes per GPU on one CartPole SE (actor %d / critic %d parameters, %d hidden "
+                               "layers of %d, B=%d, policy_delay %d), %d train episodes + per-episode test() + final test(), host-buffer entry"
+                               % (n, pa, pc, L, H, B, t.policy_delay, w["train_episodes"]),
+                   "lanes_per_gpu": n, "timing": "wall clock around le_td3_run_host (H2D + kernel + D2H), max over ranks"},
+        "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": int((0 if theta is None else theta.nbytes) + sum(x.nbytes for x in nets_n) + n * 8),
+                "d2h_bytes_per_step": int(n * (40 + pa * 4))},
+        "gpu_launches": 2 * steps, "clocks": clocks,
+        "roofline": {"bound": "fp32_ffma", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
+                     "frac": achieved / ffma_peak if ffma_peak else None, "traffic": None,
+                     "peak_source": "le_bench_ffma microbenchmark in this run"},
+    }
+
+
 def measure_nes(D, workload, steps, warmup, members_per_gpu=0, population=0, lane_override=(), ffma_peak=None, with_e2e=True):
     """One NES-generation workload on this process group: device-timed `value`, the generation including the score exchange
     and the NES update (`with_update`), and (with_e2e) the end-to-end figure through the host API.  Returns the JSON fields."""
@@ -592,7 +662,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cartpole_se", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cartpole_se", choices=sorted(WORKLOADS) + ["td3_discrete"])
     ap.add_argument("--members-per-gpu", type=int, default=0)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --population members split over the ranks")
     ap.add_argument("--population", type=int, default=0, help="total NES population for --scaling strong (default 8 x 1184)")
@@ -611,6 +681,9 @@ def main():
     extras = args.extras == "all" or (args.extras == "auto" and plain and not args.no_cpu_baseline)
     if args.workload == "vary_hp":
         line = measure_vary_hp(D, args.steps, args.warmup, args.members_per_gpu, ffma_peak)
+        cfg = None
+    elif args.workload == "td3_discrete":
+        line = measure_td3(D, args.steps, args.warmup, args.members_per_gpu, ffma_peak)
         cfg = None
     else:
         pop = (args.population or STRONG_POPULATION) if args.scaling == "strong" else 0
@@ -631,6 +704,10 @@ def main():
                         wl[name]["us_per_env_step_per_lane"] = 1e3 * r["ms_per_step"] / max(r["value"] * r["ms_per_step"] * 1e-3 / (3 * 16 * D.world), 1.0)
             except Exception as e:   # a failing side workload must not lose the headline line
                 wl[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            wl["td3_discrete"] = compact(measure_td3(D, 1, 1, 0, ffma_peak))
+        except Exception as e:
+            wl["td3_discrete"] = {"error": "%s: %s" % (type(e).__name__, e)}
         line["workloads"] = wl
         try:
             r, _ = measure_nes(D, args.workload, 2, 1, 0, STRONG_POPULATION, (), ffma_peak, with_e2e=False)
