@@ -58,7 +58,7 @@ WORKLOADS = {
     "cartpole_se_pop16": dict(cfg="cartpole_syn_env", kind="se", members_per_gpu=16, train_episodes=10),
 }
 # (f)2: TD3_discrete_vary lanes (le_td3.cu, CTA-per-lane) on the CartPole SE with the yaml's td3_discrete_vary section; host-buffer entry
-TD3_WORKLOAD = dict(cfg="cartpole_syn_env", lanes_per_gpu=592, train_episodes=3, init_episodes=1)
+TD3_WORKLOAD = dict(cfg="cartpole_syn_env", lanes_per_gpu=296, train_episodes=3, init_episodes=1)
 EXTRA_WORKLOADS = ["acrobot_se", "cartpole_rn", "cartpole_se_dueling", "acrobot_se_dueling", "acrobot_se_dueling_tc", "sweep_h1024",
                    "cartpole_se_fullring", "cartpole_se_pop16", "vary_hp"]
 STRONG_POPULATION = 8 * 1184

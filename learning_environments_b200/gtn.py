@@ -148,6 +148,7 @@ class GTN_Master(GTN_Base):
                                            mirrored=self.mirrored_sampling, **({"device": device} if device is not None else {}))
         self.theta = linear_theta(self.synthetic_env_orig.env).cpu().contiguous()
         self.generation = 0
+        self._generation_base = 0     # generations of earlier run() calls: a second run() continues the Philox generation counter
         if self.verbose and self.rank == 0:
             print('Starting GTN Master with bohb_id {} ({} members on {} rank(s))'.format(bohb_id, self.num_workers, self.world))
 
@@ -222,7 +223,7 @@ class GTN_Master(GTN_Base):
         mean_score_orig_list = []
         for it in range(self.max_iterations):
             t1 = time.time()
-            self.generation = it
+            self.generation = self._generation_base + it
             self.evaluate_population()
             mean_score = np.mean(self.score_orig_list)
             mean_score_orig_list.append(mean_score)
@@ -234,6 +235,7 @@ class GTN_Master(GTN_Base):
             self.score_transform()
             self.update_env()
             self.print_statistics(it=it, time_elapsed=time.time() - t1)
+        self._generation_base = self.generation + 1 if self.max_iterations > 0 else self._generation_base
         if self.verbose and self.rank == 0:
             print('Master quitting')
         if len(mean_score_orig_list) > 0:
@@ -262,6 +264,10 @@ class GTN_Master(GTN_Base):
         torch.save(save_dict, save_path)
 
     def calc_worker_timeout(self):
+        """agents/GTN_master.py: `time_max` for the first generation, then mean(worker wall time) * time_mult.  Kept for the
+        contract; NOT fed back into the lanes: the figure is the wall time of a CPU worker process, and the lanes of one launch
+        finish together in milliseconds, so a budget derived from it would cut every agent off.  A fixed per-agent budget is the
+        constructor's `step_budget` (env steps)."""
         if self.time_elapsed_list[0] is None:
             return self.time_max
         return statistics.mean(self.time_elapsed_list) * self.time_mult
