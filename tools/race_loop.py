@@ -14,8 +14,9 @@ from learning_environments_b200._abi import ENV_SE  # noqa: E402
 from oracle import philox  # noqa: E402
 
 
-def run(agent, over, n_lanes, tc=False):
+def run(agent, over, n_lanes, tc=False, mw=False):
     os.environ["LE_TC"] = "1" if tc else "0"
+    os.environ["LE_MW"] = "1" if mw else "0"
     d = default_configs.get("cartpole_syn_env")
     d["agents"][agent].update(dict(dict(train_episodes=2, test_episodes=2, init_episodes=1, batch_size=24), **over))
     cfg = config.lane_cfg(d, agent, ENV_SE)
@@ -27,7 +28,7 @@ def run(agent, over, n_lanes, tc=False):
     ops.inner_loop_run(bufs, cfg, torch.from_numpy(theta).cuda(), None, ops.keys_tensor(keys, "cuda"))
     torch.cuda.synchronize()
     res = bufs.results()
-    print(agent, over, "tc" if tc else "", "lanes", n_lanes, "steps", int(res["train_steps"].sum()), "learn", int(res["learn_iters"].sum()))
+    print(agent, over, "tc" if tc else "", "mw" if mw else "", "lanes", n_lanes, "steps", int(res["train_steps"].sum()), "learn", int(res["learn_iters"].sum()))
 
 
 if __name__ == "__main__":
@@ -35,6 +36,9 @@ if __name__ == "__main__":
     if which in ("all", "fused"):
         run("ddqn", {}, 6)
         run("ddqn", dict(hidden_size=100), 3)
+    if which in ("all", "mw"):     # multi-warp lanes: named barriers, shared weight records, gradient exchange (3 passes of 32 rows)
+        run("ddqn", dict(batch_size=70), 3, mw=True)
+        run("ddqn", dict(hidden_size=100, batch_size=70), 2, mw=True)
     if which in ("all", "general"):
         run("duelingddqn", dict(hidden_size=32, feature_dim=32), 2)
     if which in ("all", "tc"):
