@@ -540,7 +540,13 @@ int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* 
     P.work_counter = counter;
     if (trace_host && trace_host->cap > 0) { P.trace = *trace_host; P.trace_lane = trace_lane; }
     if (pl.general) LE_CUDA_CHECK(general_launch(c, P, P.rings, pl.gp, st));
-    else if (pl.mw) LE_CUDA_CHECK(pl.ops->launch_inner_mw(P, pl.grid, st));
+    else if (pl.mw) {
+        // the member's SE / RN pack is staged in the CTA's shared memory by one TMA bulk copy per lane when it fits beside the lane state
+        const int64_t pack_bytes = c->env_kind == LE_ENV_REAL ? 0 : pl.pack_stride_f * 4;
+        const char* e = getenv("LE_MW_PACK");
+        if (pack_bytes > 0 && pl.ops->mw_smem_bytes + pack_bytes <= 227 * 1024 && !(e && e[0] == '0')) P.mw_pack_f4 = (int)(pack_bytes / 16);
+        LE_CUDA_CHECK(pl.ops->launch_inner_mw(P, pl.grid, st));
+    }
     else LE_CUDA_CHECK(pl.ops->launch_inner(P, pl.grid, st));
     return LE_OK;
 }

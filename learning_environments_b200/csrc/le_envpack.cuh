@@ -128,7 +128,14 @@ __global__ void pack_rn_kernel(const float* __restrict__ theta, int P_env, int n
 }
 
 // ---- VirtualEnv.step for one row held replicated in registers (envs/virtual_env.py:43-54) ---------------
-template <int SD, int AD>
+// SH: `pack` points to a shared-memory copy of the pack (multi-warp lanes stage it once per lane with a TMA bulk copy): plain loads
+// instead of ld.global.nc
+template <bool SH>
+__device__ __forceinline__ float4 pack_ld4(const float4* p) { if constexpr (SH) return *p; else return __ldg(p); }
+template <bool SH>
+__device__ __forceinline__ float pack_ld1(const float* p) { if constexpr (SH) return *p; else return __ldg(p); }
+
+template <int SD, int AD, bool SH = false>
 __device__ __forceinline__ void se_step_row(const float4* __restrict__ pack, int H, bool is_tanh, const float (&s)[SD],
                                             int action, int lane, float (&ns)[SD], float& reward, float& done) {
     using P = SePack<SD, AD>;
@@ -140,7 +147,7 @@ __device__ __forceinline__ void se_step_row(const float4* __restrict__ pack, int
         float rec[P::REC];
 #pragma unroll
         for (int q = 0; q < P::RQ; ++q) {
-            const float4 v = __ldg(pack + ((int64_t)k * P::RQ + q) * 32 + lane);
+            const float4 v = pack_ld4<SH>(pack + ((int64_t)k * P::RQ + q) * 32 + lane);
             rec[4 * q + 0] = v.x; rec[4 * q + 1] = v.y; rec[4 * q + 2] = v.z; rec[4 * q + 3] = v.w;
         }
         // input = cat(one_hot(action), state): the one-hot picks one action column of W1
@@ -156,7 +163,7 @@ __device__ __forceinline__ void se_step_row(const float4* __restrict__ pack, int
     }
     const float* tail = reinterpret_cast<const float*>(pack + (int64_t)K * P::RQ * 32);
 #pragma unroll
-    for (int o = 0; o < P::NOUT; ++o) acc[o] = warp_allreduce_sum(acc[o]) + __ldg(tail + o);
+    for (int o = 0; o < P::NOUT; ++o) acc[o] = warp_allreduce_sum(acc[o]) + pack_ld1<SH>(tail + o);
 #pragma unroll
     for (int i = 0; i < SD; ++i) ns[i] = acc[i];
     reward = acc[SD];
@@ -164,7 +171,7 @@ __device__ __forceinline__ void se_step_row(const float4* __restrict__ pack, int
 }
 
 // ---- the RN potential Phi(s), Phi(s') (envs/reward_env.py:84-110) ---------------------------------------
-template <int SD>
+template <int SD, bool SH = false>
 __device__ __forceinline__ void rn_phi2(const float4* __restrict__ pack, int H, bool is_tanh, const float (&s)[SD],
                                         const float (&s2)[SD], int lane, float& phi_s, float& phi_s2) {
     using P = RnPack<SD>;
@@ -174,7 +181,7 @@ __device__ __forceinline__ void rn_phi2(const float4* __restrict__ pack, int H, 
         float rec[P::REC];
 #pragma unroll
         for (int q = 0; q < P::RQ; ++q) {
-            const float4 v = __ldg(pack + ((int64_t)k * P::RQ + q) * 32 + lane);
+            const float4 v = pack_ld4<SH>(pack + ((int64_t)k * P::RQ + q) * 32 + lane);
             rec[4 * q + 0] = v.x; rec[4 * q + 1] = v.y; rec[4 * q + 2] = v.z; rec[4 * q + 3] = v.w;
         }
         float z0 = rec[P::OFF_B1], z1 = rec[P::OFF_B1];
@@ -183,7 +190,7 @@ __device__ __forceinline__ void rn_phi2(const float4* __restrict__ pack, int H, 
         a0 = fmaf(env_act(z0, is_tanh, rec[P::OFF_SLOPE]), rec[P::OFF_W2], a0);
         a1 = fmaf(env_act(z1, is_tanh, rec[P::OFF_SLOPE]), rec[P::OFF_W2], a1);
     }
-    const float b2 = __ldg(reinterpret_cast<const float*>(pack + (int64_t)K * P::RQ * 32));
+    const float b2 = pack_ld1<SH>(reinterpret_cast<const float*>(pack + (int64_t)K * P::RQ * 32));
     phi_s = warp_allreduce_sum(a0) + b2;
     phi_s2 = warp_allreduce_sum(a1) + b2;
 }

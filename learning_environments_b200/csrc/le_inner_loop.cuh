@@ -21,6 +21,7 @@ struct RunParams {
     int rew_stride, test_stride;
     float* rings; int64_t ring_stride; int ring_cap;  // one replay ring per resident warp slot
     int* work_counter;
+    int mw_pack_f4;   // multi-warp lanes: float4s of ONE env pack to stage in shared memory per lane (0: read it from global memory)
     le_trace trace; int trace_lane;
 };
 
@@ -98,7 +99,20 @@ struct MwShared {
     int lane_id, rb_size, pad;
     long long learn_iters;
     float b2[4], tb2[4];     // output biases of the online / target net (registers of the leader)
+    unsigned long long pack_mbar;   // mbarrier of the TMA bulk copy that stages the lane's SE / RN pack
 };
+// TMA bulk copy global -> shared memory, completion on an mbarrier (cp.async.bulk; SASS UBLKCP + SYNCS)
+__device__ __forceinline__ void mbar_init(uint32_t mbar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tLE_MBAR_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LE_MBAR_DONE_%=;\n\tbra LE_MBAR_WAIT_%=;\n\tLE_MBAR_DONE_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
 template <int W>
 __device__ __forceinline__ void mw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(W * 32) : "memory"); }
 template <int U> constexpr int mw_warps() { return U <= 2 ? 8 : (U <= 4 ? 6 : 4); }
@@ -275,7 +289,8 @@ struct FusedLane {
         return sum / (double)c.test_episodes;  // statistics.mean
     }
 
-    static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane, MwShared* sh = nullptr, float* ex = nullptr) {
+    static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane, MwShared* sh = nullptr, float* ex = nullptr,
+                               float4* pack_smem = nullptr, uint32_t pack_parity = 0) {
         using SL = StageLayout<SD>;
         float* mv = smem + SW::OFF_MV;
         {   // lane configuration -> shared memory (read on demand instead of pinning ~46 registers)
@@ -287,6 +302,24 @@ struct FusedLane {
         const le_lane_cfg& c = *reinterpret_cast<const le_lane_cfg*>(smem + SW::OFF_CFG);
         const uint32_t k0 = P.keys[2 * lane_id], k1 = P.keys[2 * lane_id + 1];
         const float4* pack = P.env_pack + (int64_t)(P.env_index ? P.env_index[lane_id] : 0) * P.env_pack_stride;
+        constexpr bool kPackSh = W > 1;     // multi-warp lanes: the SE / RN pack is staged in shared memory when it fits (else W == 1 code path below)
+        bool pack_staged = false;
+        if constexpr (W > 1) {
+            if (P.mw_pack_f4 > 0 && pack_smem != nullptr) {
+                // one TMA bulk copy per lane: weights of the member's SE / RN stay on chip for the whole calc_score
+                const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sh->pack_mbar);
+                const uint32_t bytes = (uint32_t)P.mw_pack_f4 * 16u;
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of the buffer are done
+                    mbar_expect_tx(mbar, bytes);
+                    bulk_g2s((uint32_t)__cvta_generic_to_shared(pack_smem), pack, bytes, mbar);
+                }
+                mbar_wait(mbar, pack_parity);
+                pack = pack_smem;
+                pack_staged = true;
+            }
+        }
         const bool env_tanh = c.env_act == LE_ACT_TANH;
         const int H = c.q_hidden;
         float* ring = P.rings + (int64_t)slot * P.ring_stride;
@@ -345,13 +378,15 @@ struct FusedLane {
                 // ---- env.step
                 float ns[SD], r, d;
                 if (c.env_kind == LE_ENV_SE) {
-                    se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, state, action, lane, ns, r, d);
+                    if (kPackSh && pack_staged) se_step_row<SD, AD, kPackSh>(pack, c.env_hidden, env_tanh, state, action, lane, ns, r, d);
+                    else se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, state, action, lane, ns, r, d);
                     // same_action_num > 1 (envs/env_wrapper.py:24-30): chained SE steps, fp32 reward sum, no break on done
                     for (int k = 1; k < K; ++k) {
                         float cur[SD], rk;
 #pragma unroll
                         for (int i = 0; i < SD; ++i) cur[i] = ns[i];
-                        se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, cur, action, lane, ns, rk, d);
+                        if (kPackSh && pack_staged) se_step_row<SD, AD, kPackSh>(pack, c.env_hidden, env_tanh, cur, action, lane, ns, rk, d);
+                        else se_step_row<SD, AD>(pack, c.env_hidden, env_tanh, cur, action, lane, ns, rk, d);
                         r += rk;
                     }
                 } else {
@@ -365,7 +400,8 @@ struct FusedLane {
                         real_step<SD>(c.real_env, c.max_steps, st, elapsed, action, ns, rr, d);
                         if (c.env_kind == LE_ENV_RN && c.rn_type != 0) {
                             float ps, ps2;
-                            rn_phi2<SD>(pack, c.env_hidden, env_tanh, cur, ns, lane, ps, ps2);
+                            if (kPackSh && pack_staged) rn_phi2<SD, kPackSh>(pack, c.env_hidden, env_tanh, cur, ns, lane, ps, ps2);
+                            else rn_phi2<SD>(pack, c.env_hidden, env_tanh, cur, ns, lane, ps, ps2);
                             rk = rn_combine(c.rn_type, ls.gamma, rr, ps, ps2);
                         } else rk = rr;
                         if (K == 1) { r = rk; break; }
@@ -551,7 +587,14 @@ __global__ void __launch_bounds__(mw_warps<U>() * 32, 1) inner_loop_mw_kernel(co
     const int slot = blockIdx.x;
     float* ex = smem_dyn + FL::SW::FLOATS + (W - 1) * FL::MW_WORKER_F;
     MwShared* sh = reinterpret_cast<MwShared*>(ex + FL::MW_EX_F);
+    float4* pack_smem = reinterpret_cast<float4*>(smem_dyn + FL::MW_CTA_F);   // P.mw_pack_f4 float4s (0: not staged)
     if (warp == 0) {
+        if (lane == 0) {
+            mbar_init((uint32_t)__cvta_generic_to_shared(&sh->pack_mbar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        uint32_t pack_parity = 0;
         bool first = true;
         for (;;) {
             int lane_id = slot;
@@ -561,7 +604,8 @@ __global__ void __launch_bounds__(mw_warps<U>() * 32, 1) inner_loop_mw_kernel(co
             }
             first = false;
             if (lane_id >= P.n_lanes) break;
-            FL::run(P, lane_id, slot, smem_dyn, lane, sh, ex);
+            FL::run(P, lane_id, slot, smem_dyn, lane, sh, ex, pack_smem, pack_parity);
+            if (P.mw_pack_f4 > 0) pack_parity ^= 1u;
             __syncwarp();
         }
         if (lane == 0) sh->cmd = 0;

@@ -10,6 +10,7 @@ struct InstanceOps {
     int sd, ad, units, act;  // act: QACT_TANH / QACT_LEAKY
     int inner_warps;         // warps (= lane slots) per CTA of the fused kernel
     int mw_warps;            // warps per lane of the multi-warp (one lane per CTA) kernel; 0 if its shared memory does not fit
+    int64_t mw_smem_bytes;   // its shared memory without the staged env pack (P.mw_pack_f4 * 16 bytes are added at launch)
     cudaError_t (*launch_inner_mw)(const RunParams& P, int grid, cudaStream_t st);
     // fused persistent kernel
     int (*inner_max_ctas_per_sm)();
@@ -187,9 +188,10 @@ struct InstanceImpl {
     static constexpr bool kMwOk = kMwSmemBytes <= 227 * 1024;
     static cudaError_t launch_inner_mw(const RunParams& P, int grid, cudaStream_t st) {
         if constexpr (kMwOk) {
-            cudaError_t e = cudaFuncSetAttribute(inner_loop_mw_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMwSmemBytes);
+            const size_t smem = kMwSmemBytes + (size_t)P.mw_pack_f4 * 16;
+            cudaError_t e = cudaFuncSetAttribute(inner_loop_mw_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            inner_loop_mw_kernel<SD, AD, U, ACT><<<grid, mw_warps<U>() * 32, kMwSmemBytes, st>>>(P);
+            inner_loop_mw_kernel<SD, AD, U, ACT><<<grid, mw_warps<U>() * 32, smem, st>>>(P);
             return cudaGetLastError();
         } else return cudaErrorInvalidConfiguration;
     }
@@ -239,7 +241,7 @@ struct InstanceImpl {
         return cudaGetLastError();
     }
     static const InstanceOps* ops() {
-        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, kMwOk ? mw_warps<U>() : 0, launch_inner_mw, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
+        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, kMwOk ? mw_warps<U>() : 0, (int64_t)kMwSmemBytes, launch_inner_mw, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
                                       rn_pack_vec4, launch_pack_se, launch_pack_rn, launch_se_forward, launch_rn_reward,
                                       launch_qnet_forward, launch_td_update};
         return &o;
