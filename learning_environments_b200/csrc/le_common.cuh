@@ -49,8 +49,9 @@ constexpr int QACT_TANH = 0;   // nn.Tanh
 constexpr int QACT_LEAKY = 1;  // nn.ReLU (slope 0) / nn.LeakyReLU (slope 0.01): z > 0 ? z : slope*z
 
 // tanh as a 13/6 rational minimax on the FMA pipe + one MUFU.RCP: max relative error 4e-7 (6 ulp) against
-// fp64 tanh over the whole range (checked in tests/test_tanh_approx.py) — inside the 1e-5 parity budget, and
-// ~3x cheaper than libdevice tanhf.  tanh.approx.f32 (MUFU.TANH, 2^-11) is NOT accurate enough.
+// fp64 tanh over the whole range — inside the 1e-5 parity budget.  Used by the SE / RN mat-vecs (env_act); the Q-net
+// kernels use tanh_pair / tanh_one of le_lane.cuh (1 - 2 / (1 + 2^(2x log2 e)) on MUFU.EX2 / MUFU.RCP, abs error
+// <= 2.4e-7).  tanh.approx.f32 (MUFU.TANH, 2^-11) is NOT accurate enough.
 __device__ __forceinline__ float tanh_rational(float x) {
     x = fminf(fmaxf(x, -7.90531110763549805f), 7.90531110763549805f);
     const float x2 = x * x;

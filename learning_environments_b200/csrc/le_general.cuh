@@ -2,9 +2,10 @@
 //   Critic_DuelingDQN (models/actor_critic.py:94-122, 11.5k .. 67k parameters), Critic_DQN with two hidden layers or
 //   more than 128 hidden units (DDQN_vary tails, agents/DDQN_vary.py:26-59).
 // One CTA (256 threads) owns one lane; parameters, Adam state, gradients and the minibatch activations live in the
-// lane slot's HBM workspace (L2-resident: <= 2.5 MB per slot) and every dense layer is a 64x64x16 shared-memory-tiled
-// FFMA GEMM with a 4x4 register tile per thread (forward NT, input-gradient NN, weight-gradient TN through one
-// strided routine).  The control flow (episodes, eps-greedy, env step, replay ring, tests, early-out) mirrors
+// lane slot's HBM workspace (<= 2.5 MB per slot) and every dense layer with more than 16 rows is a 128x64x16
+// shared-memory-tiled GEMM with an 8x4 register tile of packed fp32x2 accumulators per thread, operands streamed by cp.async
+// (forward NT, input-gradient NN, weight-gradient TN through one strided routine; LE_TC=1: the tcgen05 routine of le_tc.cuh);
+// <= 16 rows (acting, batched test rollouts) take a thin thread-per-column path.  The control flow (episodes, eps-greedy, env step, replay ring, tests, early-out) mirrors
 // le_inner_loop.cuh; scalars are computed redundantly by all threads (uniform), warp 0 runs the SE/RN mat-vec.
 //
 // Dueling coupling (models/actor_critic.py:121): q = V + (A - A.mean()) with the mean over the WHOLE batch tensor, so
