@@ -103,6 +103,12 @@ def test_ddqn_train_and_test_match_oracle_lane(le):
     assert not np.array_equal(agent.model.net[0].weight.detach().cpu().numpy().reshape(-1), q0[:228])   # module views the flat tensor
     # replay buffer returned by train(): first transition starts from the first reset state
     assert rb.state.shape[1] == 4 and float(rb.action[:rb.size].max()) <= 1.0
+    # ... and it is THIS lane's ring (slot = lane id, warp-per-lane and multi-warp kernels alike), not uninitialised workspace:
+    # inside the first episode every row continues the previous one, and every stored value is finite
+    L0 = int(lengths[0])
+    assert L0 >= 2 and np.array_equal(rb.next_state[:L0 - 1].cpu().numpy(), rb.state[1:L0].cpu().numpy())
+    assert np.isfinite(rb.state[:rb.size].cpu().numpy()).all() and np.isfinite(rb.reward[:rb.size].cpu().numpy()).all()
+    assert set(np.unique(rb.action[:rb.size].cpu().numpy())) <= {0.0, 1.0}
     test_rewards, test_lengths, _ = agent.test(env=real)
     assert len(test_rewards) == 2 and test_rewards == [float(l) for l in test_lengths]      # CartPole: reward == length
     assert set(agent.model.state_dict().keys()) == {"net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias"}
