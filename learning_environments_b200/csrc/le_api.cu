@@ -264,6 +264,7 @@ struct Plan {
     const InstanceOps* ops;
     int grid, slots, ring_cap;
     bool mw;   // multi-warp lanes: one lane per CTA
+    bool mwc;  // cluster lanes: one lane per cluster of two CTAs (two SMs)
     int64_t ring_stride_f, pack_stride_f, pack_bytes, rings_bytes, total_bytes, off_rings, off_counter;
 };
 
@@ -279,6 +280,15 @@ static bool use_mw_lanes(const InstanceOps* ops, int n_lanes, int sms) {
     return n_lanes <= 2 * sms;
 }
 
+// Cluster lanes when every lane can have two SMs to itself (the yaml's population of 16 = 48 lanes on 148 SMs): LE_MWC=0 disables.
+static bool use_mwc_lanes(const InstanceOps* ops, int n_lanes, int sms) {
+    if (ops->mwc_smem_bytes <= 0 || 2 * n_lanes > sms) return false;
+    const char* e = getenv("LE_MW");
+    if (e && e[0] == '0') return false;
+    const char* c = getenv("LE_MWC");
+    return !(c && c[0] == '0');
+}
+
 static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
     { const int rc0 = check_env_cfg(c); if (rc0 != LE_OK) return rc0; }
     if (c->batch_size < 1 || c->rb_size < 1 || c->train_episodes < 0 || c->test_episodes < 1 || c->max_steps < 1 || n_lanes < 1) {
@@ -288,6 +298,7 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
     }
     pl->general = !is_register_resident(c);
     pl->mw = false;
+    pl->mwc = false;
     if (c->q_layers > 3) { le_set_error("Q-network hidden_layer=%d: the compiled kernel set covers up to 3 hidden layers", c->q_layers); return LE_EUNSUPPORTED; }
     // the env-packing / unit kernels of any kernel set with the right (sd, ad) serve the general path too
     const InstanceOps* ops = pl->general ? le_find_instance(c->sd, c->ad, 1, QACT_TANH) : instance_for(c, c->q_hidden);
@@ -307,6 +318,11 @@ static int make_plan(const le_lane_cfg* c, int n_lanes, int n_env, Plan* pl) {
         pl->grid = pl->gp.grid;
         pl->slots = pl->grid;
         pl->ring_stride_f = pl->gp.slot_floats;   // one slot = ring + parameters + activations
+    } else if (use_mwc_lanes(ops, n_lanes, sms)) {
+        pl->mw = true; pl->mwc = true;
+        pl->grid = 2 * n_lanes;      // one cluster of two CTAs per lane
+        pl->slots = n_lanes;
+        pl->ring_stride_f = (int64_t)pl->ring_cap * ops->ring_row_floats();
     } else if (use_mw_lanes(ops, n_lanes, sms)) {
         pl->mw = true;
         pl->grid = n_lanes < sms ? n_lanes : sms;
@@ -544,8 +560,10 @@ int le_inner_loop_run(const le_lane_cfg* cfg_dev, int n_cfg, const le_lane_cfg* 
         // the member's SE / RN pack is staged in the CTA's shared memory by one TMA bulk copy per lane when it fits beside the lane state
         const int64_t pack_bytes = c->env_kind == LE_ENV_REAL ? 0 : pl.pack_stride_f * 4;
         const char* e = getenv("LE_MW_PACK");
-        if (pack_bytes > 0 && pl.ops->mw_smem_bytes + pack_bytes <= 227 * 1024 && !(e && e[0] == '0')) P.mw_pack_f4 = (int)(pack_bytes / 16);
-        LE_CUDA_CHECK(pl.ops->launch_inner_mw(P, pl.grid, st));
+        const int64_t lane_smem = pl.mwc ? pl.ops->mwc_smem_bytes : pl.ops->mw_smem_bytes;
+        if (pack_bytes > 0 && lane_smem + pack_bytes <= 227 * 1024 && !(e && e[0] == '0')) P.mw_pack_f4 = (int)(pack_bytes / 16);
+        if (pl.mwc) LE_CUDA_CHECK(pl.ops->launch_inner_mwc(P, pl.slots, st));
+        else LE_CUDA_CHECK(pl.ops->launch_inner_mw(P, pl.grid, st));
     }
     else LE_CUDA_CHECK(pl.ops->launch_inner(P, pl.grid, st));
     return LE_OK;

@@ -4,6 +4,7 @@
 // (agents/DDQN.py:60-95), per-episode greedy test() on the real env (agents/base_agent.py:155-227), the
 // early-out rule (agents/base_agent.py:49-62) and the final test().  Warps pull lanes from a global queue.
 #pragma once
+#include <cooperative_groups.h>
 #include "le_envpack.cuh"
 #include "le_lane.cuh"
 
@@ -116,9 +117,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 template <int W>
 __device__ __forceinline__ void mw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(W * 32) : "memory"); }
 template <int U> constexpr int mw_warps() { return U <= 2 ? 8 : (U <= 4 ? 6 : 4); }
+// Cluster lanes (CL = 2, inner_loop_mwc_kernel): ONE lane per thread-block cluster of two CTAs = two SMs.  CTA 0 holds the leader warp and
+// kMwcWarps - 1 workers, CTA 1 the same number of workers; the minibatch passes alternate between the two SMs (one working warp per
+// scheduler), the weight records and the command block are replicated into CTA 1 through distributed shared memory, the workers of CTA 1
+// write their gradient sums straight into CTA 0's exchange buffer, and the two barriers of a learn() are cluster barriers.
+constexpr int kMwcWarps = 5;
+__device__ __forceinline__ void cluster_bar() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
-template <int SD, int AD, int U, int ACT, int W = 1>
+template <int SD, int AD, int U, int ACT, int W = 1, int CL = 1>
 struct FusedLane {
+    static constexpr int NPART = CL == 1 ? W : 2 * (W - 1);          // participants of a learn(): pass p goes to participant p % NPART
+    static constexpr int NEXS = CL == 1 ? W - 1 : NPART;             // exchange slots (CL == 1: the leader keeps its share in registers)
+    static __device__ __forceinline__ void lane_bar(int id) { if constexpr (CL == 1) mw_bar<W>(id); else cluster_bar(); }
     using Core = LaneCore<SD, AD, U, ACT, (W > 1 ? 1 : -1)>;
     using RL = RowLayout<SD>;
     using SW = SmemWarp<SD, AD, U, (W > 1 ? 1 : -1)>;
@@ -127,20 +139,20 @@ struct FusedLane {
     static constexpr int MW_STAGE_F = 32 * SL0::STAGE_F;
     static constexpr int MW_WORKER_F = MW_STAGE_F + Core::ROW_SCRATCH_F;
     static constexpr int MW_NEX = U * (SD + 1 + AD) + AD + 1;
-    static constexpr int MW_EX_F = (W - 1) * MW_NEX * 32;
+    static constexpr int MW_EX_F = NEXS * MW_NEX * 32;
     static constexpr int MW_SH_F = (sizeof(MwShared) + 15) / 16 * 4;
     static constexpr int MW_CTA_F = SW::FLOATS + (W - 1) * MW_WORKER_F + MW_EX_F + MW_SH_F;
 
     // This warp's share of one DDQN.learn: passes w, w + W, ... of 32 sampled rows each (same Philox blocks as the single-warp
     // gather: block = row / 4 of the minibatch).  Gradients accumulate in core.a*, returns the warp's share of sum(delta^2).
-    static __device__ __forceinline__ float mw_td_share(Core& core, int w, const float* wrec, float* stage, float* scratch, const float* ring,
+    static __device__ __forceinline__ float mw_td_share(Core& core, int part, const float* wrec, float* stage, float* scratch, const float* ring,
                                                         int rb_size, long long learn_iters, uint32_t k0, uint32_t k1, const LearnScalars& ls, int lane) {
         core.zero_grads();
         float loss_part = 0.f;
         const int B = ls.batch;
         const int npass = (B + 31) >> 5;
         const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
-        for (int p = w; p < npass; p += W) {
+        for (int p = part; p < npass; p += NPART) {
             const int nrows = min(32, B - 32 * p);
             if (lane < 8) {
                 const u32x4 wv = philox4x32_10((uint32_t)learn_iters, (uint32_t)(8 * p + lane), LE_P_SAMPLE, 0u, k0, k1);
@@ -168,18 +180,21 @@ struct FusedLane {
         return loss_part;
     }
     // worker warps of a multi-warp lane
-    static __device__ void mw_worker(const RunParams& P, int slot, int w, float* lead_smem, float* my_smem, MwShared* sh, float* ex, int lane) {
+    // lead_smem: THIS CTA's copy of the leader region (weight records); ex / cfgp: the exchange buffer and lane configuration of the
+    // leader's CTA (distributed shared memory for the workers of CTA 1)
+    static __device__ void mw_worker(const RunParams& P, int slot, int w, int part, float* lead_smem, float* my_smem, MwShared* sh, float* ex,
+                                     const le_lane_cfg* cfgp, int lane) {
         Core core;
         core.bind(lead_smem + SW::OFF_RED, lane);
         float* stage = my_smem;
         float* scratch = my_smem + MW_STAGE_F;
         Core::init_row_scratch(scratch, lane);
         const float* ring = P.rings + (int64_t)slot * P.ring_stride;
-        const le_lane_cfg& c = *reinterpret_cast<const le_lane_cfg*>(lead_smem + SW::OFF_CFG);
+        const le_lane_cfg& c = *cfgp;
         LearnScalars ls;
         uint32_t k0 = 0, k1 = 0;
         for (;;) {
-            mw_bar<W>(1);
+            lane_bar(1);
             const int cmd = sh->cmd;
             if (cmd == 0) break;
             if (cmd == 2) {
@@ -189,8 +204,8 @@ struct FusedLane {
 #pragma unroll
                 for (int a = 0; a < AD; ++a) { core.b2[a] = sh->b2[a]; core.tb2[a] = sh->tb2[a]; }
                 core.publish_weights(nullptr, lane);
-                const float lp = mw_td_share(core, w, lead_smem + SW::OFF_RED, stage, scratch, ring, sh->rb_size, sh->learn_iters, k0, k1, ls, lane);
-                float* e = ex + (w - 1) * MW_NEX * 32 + lane;
+                const float lp = mw_td_share(core, part, lead_smem + SW::OFF_RED, stage, scratch, ring, sh->rb_size, sh->learn_iters, k0, k1, ls, lane);
+                float* e = ex + (CL == 1 ? w - 1 : part) * MW_NEX * 32 + lane;
                 int k = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -204,7 +219,7 @@ struct FusedLane {
                 for (int a = 0; a < AD; ++a) e[32 * (k++)] = core.gb2[a];
                 e[32 * k] = lp;
             }
-            mw_bar<W>(2);
+            lane_bar(2);
         }
     }
 
@@ -290,7 +305,7 @@ struct FusedLane {
     }
 
     static __device__ void run(const RunParams& P, int lane_id, int slot, float* smem, int lane, MwShared* sh = nullptr, float* ex = nullptr,
-                               float4* pack_smem = nullptr, uint32_t pack_parity = 0) {
+                               float4* pack_smem = nullptr, uint32_t pack_parity = 0, MwShared* sh_r = nullptr, float* wrec_r = nullptr) {
         using SL = StageLayout<SD>;
         float* mv = smem + SW::OFF_MV;
         {   // lane configuration -> shared memory (read on demand instead of pinning ~46 registers)
@@ -336,13 +351,24 @@ struct FusedLane {
         core.copy_online_to_target();  // model_target.load_state_dict(model.state_dict())   agents/DDQN.py:36
         Core::init_row_region(smem + SW::OFF_RED, lane);
         core.publish_weights(smem + SW::OFF_RED, lane);
+        auto replicate_weights = [&]() {   // cluster lanes: CTA 1 reads its own copy of the weight records
+            if constexpr (CL > 1) {
+                const float4* src = reinterpret_cast<const float4*>(smem + SW::OFF_RED);
+                float4* dst = reinterpret_cast<float4*>(wrec_r);
+                for (int k = lane; k < Core::ROW_WREC_F / 4; k += 32) dst[k] = src[k];
+            }
+        };
+        replicate_weights();
         Core::zero_moments(mv, lane);
         LearnScalars ls;
         fill_learn_scalars(ls, c);
         if constexpr (W > 1) {   // workers pick up the lane's configuration and keys
-            if (lane == 0) { sh->cmd = 2; sh->lane_id = lane_id; }
-            mw_bar<W>(1);
-            mw_bar<W>(2);
+            if (lane == 0) {
+                sh->cmd = 2; sh->lane_id = lane_id;
+                if constexpr (CL > 1) { sh_r->cmd = 2; sh_r->lane_id = lane_id; }
+            }
+            lane_bar(1);
+            lane_bar(2);
         }
 
         int rb_ptr = 0, rb_size = 0;
@@ -438,15 +464,20 @@ struct FusedLane {
                     const int B = ls.batch;
                     if constexpr (W > 1) {
                         if (lane == 0) {
-                            sh->cmd = 1; sh->rb_size = rb_size; sh->learn_iters = learn_iters;
+                            auto msg = [&](MwShared* m) {
+                                m->cmd = 1; m->rb_size = rb_size; m->learn_iters = learn_iters;
 #pragma unroll
-                            for (int a = 0; a < AD; ++a) { sh->b2[a] = core.b2[a]; sh->tb2[a] = core.tb2[a]; }
+                                for (int a = 0; a < AD; ++a) { m->b2[a] = core.b2[a]; m->tb2[a] = core.tb2[a]; }
+                            };
+                            msg(sh);
+                            if constexpr (CL > 1) msg(sh_r);
                         }
-                        mw_bar<W>(1);     // the appended row, the weights and the command are visible to every warp of the lane
-                        loss_part = mw_td_share(core, 0, smem + SW::OFF_RED, smem, smem + SW::OFF_RED + Core::ROW_WREC_F, ring, rb_size, learn_iters, k0, k1, ls, lane);
-                        mw_bar<W>(2);     // every warp's gradients are in the exchange buffer: add them in warp order
-                        for (int w = 1; w < W; ++w) {
-                            const float* e = ex + (w - 1) * MW_NEX * 32 + lane;
+                        lane_bar(1);     // the appended row, the weights and the command are visible to every warp of the lane
+                        if constexpr (CL == 1) loss_part = mw_td_share(core, 0, smem + SW::OFF_RED, smem, smem + SW::OFF_RED + Core::ROW_WREC_F, ring, rb_size, learn_iters, k0, k1, ls, lane);
+                        else core.zero_grads();
+                        lane_bar(2);     // every participant's gradients are in the exchange buffer: add them in participant order
+                        for (int w = 0; w < NEXS; ++w) {
+                            const float* e = ex + w * MW_NEX * 32 + lane;
                             int k = 0;
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
@@ -504,6 +535,7 @@ struct FusedLane {
                     loss = warp_allreduce_sum(loss_part) / (float)B;
                     core.adam_polyak(ls, mv, lane);
                     core.publish_weights(smem + SW::OFF_RED, lane);
+                    if constexpr (W > 1) replicate_weights();
                     learn_iters += 1;
                 }
                 if (tracing && train_steps < P.trace.cap && lane == 0) {
@@ -611,8 +643,64 @@ __global__ void __launch_bounds__(mw_warps<U>() * 32, 1) inner_loop_mw_kernel(co
         if (lane == 0) sh->cmd = 0;
         mw_bar<W>(1);
     } else {
-        FL::mw_worker(P, slot, warp, smem_dyn, smem_dyn + FL::SW::FLOATS + (warp - 1) * FL::MW_WORKER_F, sh, ex, lane);
+        FL::mw_worker(P, slot, warp, warp, smem_dyn, smem_dyn + FL::SW::FLOATS + (warp - 1) * FL::MW_WORKER_F, sh, ex,
+                      reinterpret_cast<const le_lane_cfg*>(smem_dyn + FL::SW::OFF_CFG), lane);
     }
+}
+
+// Cluster lanes: one lane per thread-block cluster of two CTAs (two SMs), see kMwcWarps above.  Launched with cluster dimension 2.
+template <int SD, int AD, int U, int ACT>
+__global__ void __launch_bounds__(kMwcWarps * 32, 1) inner_loop_mwc_kernel(const RunParams P) {
+    namespace cg = cooperative_groups;
+    constexpr int W = kMwcWarps;
+    using FL = FusedLane<SD, AD, U, ACT, W, 2>;
+    extern __shared__ __align__(16) float smem_dyn[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x >> 1, n_slots = gridDim.x >> 1;
+    float* ex = smem_dyn + FL::SW::FLOATS + (W - 1) * FL::MW_WORKER_F;
+    MwShared* sh = reinterpret_cast<MwShared*>(ex + FL::MW_EX_F);
+    float4* pack_smem = reinterpret_cast<float4*>(smem_dyn + FL::MW_CTA_F);
+    // the same offsets in the other CTA of the cluster (distributed shared memory)
+    float* smem_0 = cluster.map_shared_rank(smem_dyn, 0);
+    float* smem_1 = cluster.map_shared_rank(smem_dyn, 1);
+    float* ex_0 = smem_0 + (ex - smem_dyn);
+    MwShared* sh_1 = reinterpret_cast<MwShared*>(smem_1 + (reinterpret_cast<float*>(sh) - smem_dyn));
+    cluster_bar();   // both CTAs of the cluster are running before either touches the other's shared memory
+    if (rank == 0 && warp == 0) {
+        if (lane == 0) {
+            mbar_init((uint32_t)__cvta_generic_to_shared(&sh->pack_mbar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        uint32_t pack_parity = 0;
+        bool first = true;
+        for (;;) {
+            int lane_id = slot;
+            if (!first) {
+                if (lane == 0) lane_id = n_slots + atomicAdd(P.work_counter, 1);
+                lane_id = __shfl_sync(LE_FULL_MASK, lane_id, 0);
+            }
+            first = false;
+            if (lane_id >= P.n_lanes) break;
+            FL::run(P, lane_id, slot, smem_dyn, lane, sh, ex, pack_smem, pack_parity, sh_1, smem_1 + FL::SW::OFF_RED);
+            if (P.mw_pack_f4 > 0) pack_parity ^= 1u;
+            __syncwarp();
+        }
+        if (lane == 0) { sh->cmd = 0; sh_1->cmd = 0; }
+        cluster_bar();
+    } else if (warp >= 1) {
+        FL::mw_worker(P, slot, warp, 2 * (warp - 1) + rank, smem_dyn, smem_dyn + FL::SW::FLOATS + (warp - 1) * FL::MW_WORKER_F, sh, ex_0,
+                      reinterpret_cast<const le_lane_cfg*>(smem_0 + FL::SW::OFF_CFG), lane);
+    } else {   // warp 0 of CTA 1: follows the barriers
+        for (;;) {
+            cluster_bar();
+            if (sh->cmd == 0) break;
+            cluster_bar();
+        }
+    }
+    cluster_bar();   // no CTA leaves while the other may still touch its shared memory
 }
 
 }  // namespace le

@@ -11,6 +11,8 @@ struct InstanceOps {
     int inner_warps;         // warps (= lane slots) per CTA of the fused kernel
     int mw_warps;            // warps per lane of the multi-warp (one lane per CTA) kernel; 0 if its shared memory does not fit
     int64_t mw_smem_bytes;   // its shared memory without the staged env pack (P.mw_pack_f4 * 16 bytes are added at launch)
+    int64_t mwc_smem_bytes;  // cluster lanes (one lane per cluster of two CTAs): shared memory per CTA, 0 if not compiled for this kernel set
+    cudaError_t (*launch_inner_mwc)(const RunParams& P, int n_slots, cudaStream_t st);
     cudaError_t (*launch_inner_mw)(const RunParams& P, int grid, cudaStream_t st);
     // fused persistent kernel
     int (*inner_max_ctas_per_sm)();
@@ -195,6 +197,23 @@ struct InstanceImpl {
             return cudaGetLastError();
         } else return cudaErrorInvalidConfiguration;
     }
+    using MwcLane = FusedLane<SD, AD, U, ACT, kMwcWarps, 2>;
+    static constexpr size_t kMwcSmemBytes = (size_t)MwcLane::MW_CTA_F * sizeof(float);
+    static constexpr bool kMwcOk = U <= 4 && kMwcSmemBytes <= 200 * 1024;
+    static cudaError_t launch_inner_mwc(const RunParams& P, int n_slots, cudaStream_t st) {
+        if constexpr (kMwcOk) {
+            const size_t smem = kMwcSmemBytes + (size_t)P.mw_pack_f4 * 16;
+            cudaError_t e = cudaFuncSetAttribute(inner_loop_mwc_kernel<SD, AD, U, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * n_slots); cfg.blockDim = dim3(kMwcWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, inner_loop_mwc_kernel<SD, AD, U, ACT>, P);
+        } else return cudaErrorInvalidConfiguration;
+    }
     static int64_t ring_row_floats() { return RowLayout<SD>::ROWF; }
     static int64_t se_pack_vec4(int H) { return SePack<SD, AD>::pack_vec4(H); }
     static int64_t rn_pack_vec4(int H) { return RnPack<SD>::pack_vec4(H); }
@@ -241,7 +260,7 @@ struct InstanceImpl {
         return cudaGetLastError();
     }
     static const InstanceOps* ops() {
-        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, kMwOk ? mw_warps<U>() : 0, (int64_t)kMwSmemBytes, launch_inner_mw, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
+        static const InstanceOps o = {SD, AD, U, ACT, kInnerWarps, kMwOk ? mw_warps<U>() : 0, (int64_t)kMwSmemBytes, kMwcOk ? (int64_t)kMwcSmemBytes : 0, launch_inner_mwc, launch_inner_mw, inner_max_ctas_per_sm, launch_inner, ring_row_floats, se_pack_vec4,
                                       rn_pack_vec4, launch_pack_se, launch_pack_rn, launch_se_forward, launch_rn_reward,
                                       launch_qnet_forward, launch_td_update};
         return &o;

@@ -193,6 +193,7 @@ def test_multi_warp_lanes_deterministic_and_independent_of_scheduling(ops, monke
     keys = [philox.lane_key(41, 1, i, i % 3, 0) for i in range(n)]
     env_index = (np.arange(n) % n_env).astype(np.int32)
     monkeypatch.setenv("LE_MW", "1")
+    monkeypatch.setenv("LE_MWC", "0")      # one kernel family for the 200-lane run and its 37-lane subset (cluster lanes: below)
     r1, rew1, q1 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
     r2, rew2, q2 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
     sub = rng.permutation(n)[:37]
@@ -202,6 +203,19 @@ def test_multi_warp_lanes_deterministic_and_independent_of_scheduling(ops, monke
         assert np.array_equal(r3[f], r1[f][sub]), f
     assert np.array_equal(rew1, rew2) and np.array_equal(q1, q2)
     assert np.array_equal(rew3, rew1[sub]) and np.array_equal(q3, q1[sub])
+    # cluster lanes (one lane per thread-block cluster of two CTAs; at most 74 lanes): deterministic, independent of the lane set, and
+    # against the single-CTA multi-warp lanes equal up to the order in which the participants' gradient sums are added
+    monkeypatch.setenv("LE_MWC", "1")
+    c1, crew1, cq1 = _full_size_run(ops, cfg, thetas, [keys[i] for i in sub], env_index[sub], n_env)
+    c2, crew2, cq2 = _full_size_run(ops, cfg, thetas, [keys[i] for i in sub], env_index[sub], n_env)
+    sub2 = np.arange(0, 37, 3)
+    c3, crew3, cq3 = _full_size_run(ops, cfg, thetas, [keys[sub[i]] for i in sub2], env_index[sub][sub2], n_env)
+    for f in ("n_episodes", "train_steps", "learn_iters", "test_steps", "score"):
+        assert np.array_equal(c1[f], c2[f]), f
+        assert np.array_equal(c3[f], c1[f][sub2]), f
+    assert np.array_equal(cq1, cq2) and np.array_equal(cq3, cq1[sub2])
+    csame = (c1["train_steps"] == r3["train_steps"]) & (c1["n_episodes"] == r3["n_episodes"])
+    assert csame.mean() >= 0.8 and rel_err(cq1[csame], q3[csame]) < 5e-2
     monkeypatch.setenv("LE_MW", "0")
     r0, rew0, q0 = _full_size_run(ops, cfg, thetas, keys, env_index, n_env)
     same = (r0["train_steps"] == r1["train_steps"]) & (r0["n_episodes"] == r1["n_episodes"])

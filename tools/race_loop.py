@@ -37,6 +37,11 @@ if __name__ == "__main__":
         run("ddqn", {}, 6)
         run("ddqn", dict(hidden_size=100), 3)
     if which in ("all", "mw"):     # multi-warp lanes: named barriers, shared weight records, gradient exchange (3 passes of 32 rows)
+        os.environ["LE_MWC"] = "0"
+        run("ddqn", dict(batch_size=70), 3, mw=True)
+        run("ddqn", dict(hidden_size=100, batch_size=70), 2, mw=True)
+    if which in ("all", "mwc"):    # cluster lanes: cluster barriers, weight records / command replicated and gradients exchanged through DSMEM
+        os.environ["LE_MWC"] = "1"
         run("ddqn", dict(batch_size=70), 3, mw=True)
         run("ddqn", dict(hidden_size=100, batch_size=70), 2, mw=True)
     if which in ("all", "general"):
