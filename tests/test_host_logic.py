@@ -208,6 +208,12 @@ def test_gtn_master_generation_logic_with_oracle_backend(monkeypatch, tmp_path):
     assert m.save_good_model(10.0) is True and os.path.exists(model_name)
     ck = torch.load(model_name, weights_only=False)
     assert set(ck.keys()) == {"model", "config"} and "env.state_net.0.weight" in ck["model"]
+    # a second run() continues the Philox generation counter (fresh perturbations and lane keys, not a replay of generations 0, 1)
+    seen = []
+    orig = m.evaluator.evaluate
+    m.evaluator.evaluate = lambda theta, generation: (seen.append(generation), orig(theta, generation))[1]
+    m.run()
+    assert seen == [2, 3] and m.generation == 3
 
 
 def test_gtn_master_unknown_options_raise_like_the_reference(monkeypatch, tmp_path):
